@@ -1,0 +1,147 @@
+/* pfz.h -- C ABI of libpfz.so: the B200 (sm_100a) pairwise string-similarity hot path that
+ * drops in behind PolyFuzz's BaseMatcher plugins.
+ *
+ * The reference (MaartenGr/PolyFuzz @ v0.4.3) is pure Python and has no FFI of its own; its hot
+ * path calls third-party native code through Python.  Each entry point below names the reference
+ * call site / third-party routine it replaces (file:line into the reference tree, `sk:` =
+ * scikit-learn 1.9.0).  INTEGRATION.md shows the ctypes stubs a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; buffers are caller-allocated
+ *     (PyTorch tensors in the shipped host code); the library never frees or retains them, except
+ *     for workspaces it is handed explicitly;
+ *   - every function returns 0 on success, non-zero on failure; pfz_last_error() then returns a
+ *     thread-local human-readable message (CUDA error string included);
+ *   - the last argument is the CUDA stream (cudaStream_t passed as void*); all work is enqueued on
+ *     it and nothing synchronises unless stated;
+ *   - strings travel as UTF-32 code points: `blob` (uint32) + `offsets` (int64, n+1 entries);
+ *   - there is NO CPU fallback: on a machine without an sm_100 device the calls fail.
+ */
+#ifndef PFZ_H
+#define PFZ_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFZ_ABI_VERSION 1
+
+/* flags for the n-gram analyser */
+#define PFZ_FLAG_CLEAN         1   /* _clean_string: lower, keep [a-z0-9 ], collapse spaces, strip */
+#define PFZ_FLAG_REMOVE_SPACE  2   /* drop n-grams that contain U+0020                            */
+
+/* edit-distance metrics */
+#define PFZ_METRIC_LEV       0     /* Levenshtein distance, unit costs                             */
+#define PFZ_METRIC_INDEL     1     /* |a|+|b|-2*LCS                                                */
+#define PFZ_METRIC_NORM_LEV  2     /* 1 - lev/max(|a|,|b|)                                         */
+#define PFZ_METRIC_RATIO     3     /* rapidfuzz fuzz.ratio = (1 - indel/(|a|+|b|))*100             */
+
+int         pfz_abi_version(void);
+const char *pfz_last_error(void);
+/* device properties the host code needs for launch sizing: sm_count, max dynamic smem per block */
+int pfz_device_info(int32_t *sm_count, int32_t *smem_per_block_optin, int32_t *cc_major, int32_t *cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  char-n-gram TF-IDF vectoriser.
+ * Replaces: polyfuzz/models/_tfidf.py:142-146 (_clean_string), :120-139 (_create_ngrams),
+ *           :102-118 (_extract_tf_idf) and sk:feature_extraction/text.py:1257-1320 (_count_vocab),
+ *           :1204-1216 (_sort_features), :1651-1739 (TfidfTransformer fit/transform),
+ *           sk:utils/sparsefuncs_fast.pyx:578-605 (row l2 normalise).
+ *
+ * An n-gram is represented by an order-preserving integer code: sum_i sym(c_i) * base^(nmax-1-i)
+ * with sym >= 1 (0 = "no character"), so integer order == Python string order used for sklearn's
+ * alphabetical vocabulary.  Clean mode: fixed alphabet ' '<'0'..'9'<'a'..'z' (base 38).  Raw mode:
+ * sym_table[code point] (uint32[0x110000], 0xFFFFFFFF = not in the fitted alphabet), base = A+1.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* raw mode alphabet: mark every code point that occurs (present: uint8[0x110000], pre-zeroed) */
+int pfz_alphabet_mark(const uint32_t *blob, int64_t n_chars, uint8_t *present, void *stream);
+
+/* Stage A: per string: (clean,) enumerate n-grams, sort, run-length encode.
+ *   occ_ptr[r]   (int64[n+1], host-computed upper bound prefix: sum_n max(0, len_r-n+1))
+ *   codes/tf     output at occ_ptr[r] .. occ_ptr[r]+row_cnt[r]  (codes ascending, distinct)
+ *   long_rows    (int32[n_long], rows whose slot count exceeds PFZ_WARP_ROW_SLOTS; may be NULL)      */
+#define PFZ_WARP_ROW_SLOTS 256
+#define PFZ_MAX_ROW_SLOTS  8192
+int pfz_ngram_rows(const uint32_t *blob, const int64_t *offsets, int32_t n_rows,
+                   int32_t ngram_lo, int32_t ngram_hi, int32_t flags,
+                   const uint32_t *sym_table, uint32_t base,
+                   const int64_t *occ_ptr, const int32_t *long_rows, int32_t n_long,
+                   uint64_t *codes, int32_t *tf, int32_t *row_cnt, void *stream);
+
+/* Stage B (fit), small code space (base^nmax <= 2^24): document frequency by direct addressing.
+ *   df_dense (int32[code_space], pre-zeroed) accumulates over one or more lists (call once per list) */
+int pfz_df_dense(const uint64_t *codes, const int64_t *occ_ptr, const int32_t *row_cnt, int32_t n_rows,
+                 int32_t *df_dense, void *stream);
+/*   then compact: vocab_keys (ascending codes with df>0), df (int32[V]), rank_dense (int32[code_space],
+ *   -1 = absent); *n_vocab_dev (int32 on device).  ws: >= pfz_scan_ws_bytes(code_space) bytes.         */
+int pfz_vocab_compact_dense(const int32_t *df_dense, int64_t code_space, uint64_t *vocab_keys, int32_t *df,
+                            int32_t *rank_dense, int32_t *n_vocab_dev, void *ws, void *stream);
+
+/* Stage B (fit), large code space: gather all per-row distinct codes of the fit lists into
+ * `keys` (uint64[cap_pow2], padded with ~0), sort (bitonic), unique+count.                           */
+int pfz_gather_codes(const uint64_t *codes, const int64_t *occ_ptr, const int32_t *row_cnt, int32_t n_rows,
+                     uint64_t *keys, int64_t *cursor_dev, void *stream);
+int pfz_sort_u64(uint64_t *keys, int64_t n_pow2, void *stream);
+int pfz_vocab_from_sorted(const uint64_t *sorted_keys, int64_t n_keys_cap, const int64_t *n_keys_dev,
+                          uint64_t *vocab_keys, int32_t *df, int32_t *n_vocab_dev, void *ws, void *stream);
+
+/* Stage C: emit the l2-normalised TF-IDF CSR for one list with a FIXED vocabulary (transform).
+ *   lookup: rank_dense (may be NULL) else binary search in vocab_keys[n_vocab]; OOV n-grams dropped
+ *   idf: float64[n_vocab] (computed by the host with numpy exactly as sklearn does, text.py:1679-1694)
+ *   indptr int32[n_rows+1]; indices int32[cap]; data float64[cap], cap >= occ_ptr[n_rows]
+ *   ws: >= pfz_scan_ws_bytes(n_rows+1) + 4*(n_rows+1) bytes                                           */
+int pfz_tfidf_emit(const uint64_t *codes, const int32_t *tf, const int64_t *occ_ptr, const int32_t *row_cnt,
+                   int32_t n_rows, const int32_t *rank_dense, const uint64_t *vocab_keys, int32_t n_vocab,
+                   const double *idf, int32_t *indptr, int32_t *indices, double *data, void *ws, void *stream);
+
+int64_t pfz_scan_ws_bytes(int64_t n);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  sparse cosine with fused per-row top-k.
+ * Replaces: sparse_dot_topn.awesome_cossim_topn (call site polyfuzz/models/_utils.py:82) plus
+ *           polyfuzz/models/_utils.py:84-87 (diagonal removal), :128-136 (_top_n_idx_sparse),
+ *           :139-146 (_top_n_similarities_sparse, without the 3-dp rounding which stays in the
+ *           DataFrame assembly).
+ * Canonical contract: fp64, per (from-row, to-row) products added in ascending term order, each
+ * product rounded before the add; candidate iff score > min_similarity (strict) and not the
+ * diagonal; ranking key (score desc, to-index asc); empty slots idx=-1, score=0.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Inverted index of the to-matrix: postings grouped by (term, to-tile of `tile` rows).
+ *   seg      int32[n_vocab*(n_tiles)+1]  prefix offsets, entry t*n_tiles+tau = start of (term t, tile tau)
+ *   post_idx int32[nnz]  to-row LOCAL to the shard;  post_val float64[nnz]
+ *   ws: >= pfz_scan_ws_bytes(n_vocab*n_tiles+1) + 4*(n_vocab*n_tiles+1) bytes                         */
+int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double *data, int32_t n_rows,
+                    int32_t n_vocab, int32_t tile, int32_t n_tiles,
+                    int32_t *seg, int32_t *post_idx, double *post_val, void *ws, void *stream);
+
+/* top-k of (from CSR) x (to inverted index).
+ *   k <= 32.  n_splits > 1 splits the to-tiles over blockIdx.y and writes partial lists
+ *   [n_splits][n_from][k] (then call pfz_topk_merge).  self_match: exclude global to-index ==
+ *   from_index_base + i.  Output indices are GLOBAL: to_index_base + local row.
+ *   excl_val/excl_idx (may be NULL): per-row exclusive lower key -- only candidates ranking strictly
+ *   AFTER (excl_val[i], excl_idx[i]) are considered (used to page through top_n > 32).
+ *   row_counter: int32 on device, zeroed by the callee (dynamic row scheduling).                     */
+int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from,
+                   const int32_t *seg, const int32_t *post_idx, const double *post_val,
+                   int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to,
+                   int32_t k, double min_similarity, int32_t self_match,
+                   int64_t from_index_base, int64_t to_index_base, int32_t n_splits,
+                   const double *excl_val, const int32_t *excl_idx,
+                   int32_t *top_idx, double *top_val, int32_t *row_counter, void *stream);
+
+/* merge n_lists sorted top-k lists per row ([n_lists][n_from][k_in]) into [n_from][k_out];
+ * same key.  Used for tile splits and for the per-shard lists after the NCCL all-gather.            */
+int pfz_topk_merge(const int32_t *idx, const double *val, int32_t n_lists, int32_t n_from, int32_t k_in,
+                   int32_t k_out, int32_t *out_idx, double *out_val, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * End-to-end convenience entry with HOST buffers (what a foreign-language binding would call):
+ * self- or two-list TF-IDF match, H2D + K1 + K2 + D2H inside.  See INTEGRATION.md.
+ * ---------------------------------------------------------------------------------------------- */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFZ_H */

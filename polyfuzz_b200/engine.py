@@ -1,0 +1,352 @@
+"""Device-side engine: thin Python drivers over the C ABI (include/pfz.h).  PyTorch is used only for
+device memory, streams and (in distributed.py) NCCL -- every kernel is in libpfz.so.
+
+Classes
+    NgramTfidf   K1: fit / transform of the char-n-gram TF-IDF vectoriser -> CSR tensors in HBM
+    SparseIndex  inverted index of a to-matrix (term x to-tile posting segments)
+Functions
+    spcos_topk   K2: fused sparse cosine + per-row top-k (pages of 32 for larger k), tile splits + merge
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .strings import pack_utf32, ngram_slot_bounds
+
+FLAG_CLEAN, FLAG_REMOVE_SPACE = 1, 2
+WARP_ROW_SLOTS, MAX_ROW_SLOTS = 256, 8192
+DENSE_CODE_SPACE_MAX = 1 << 24
+CLEAN_BASE = 38
+N_CODE_POINTS = 0x110000
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise RuntimeError("polyfuzz_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _to_dev(arr, dtype=None):
+    """numpy -> device tensor via pinned staging (async H2D on the current stream)."""
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if dtype is not None:
+        t = t.view(dtype)
+    if t.numel() == 0:
+        return torch.empty(0, dtype=t.dtype, device=_dev())
+    return t.pin_memory().to(_dev(), non_blocking=True)
+
+
+def _ws(nbytes):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=_dev())
+
+
+class CsrMatrix:
+    """l2-normalised TF-IDF rows in HBM: int32 indptr[n+1], int32 indices[cap], float64 data[cap]
+    (cap >= nnz; nnz = indptr[n])."""
+
+    def __init__(self, indptr, indices, data, n_rows, n_cols):
+        self.indptr, self.indices, self.data = indptr, indices, data
+        self.n_rows, self.n_cols = n_rows, n_cols
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        ip = self.indptr.cpu().numpy()
+        nnz = int(ip[-1]) if len(ip) else 0
+        return sp.csr_matrix((self.data[:nnz].cpu().numpy(), self.indices[:nnz].cpu().numpy(), ip),
+                             shape=(self.n_rows, self.n_cols))
+
+    @staticmethod
+    def from_scipy(m):
+        m = m.tocsr(); m.sort_indices()
+        return CsrMatrix(_to_dev(m.indptr.astype(np.int32)), _to_dev(m.indices.astype(np.int32)),
+                         _to_dev(m.data.astype(np.float64)), m.shape[0], m.shape[1])
+
+
+class _Rows:
+    """Stage-A result for one string list: per-row sorted distinct n-gram codes + counts."""
+    __slots__ = ("n", "occ_ptr", "codes", "tf", "row_cnt", "cap")
+
+
+class NgramTfidf:
+    """B200 statement of `TfidfVectorizer(min_df=1, analyzer=TFIDF._create_ngrams)` as the reference
+    uses it (polyfuzz/models/_tfidf.py:102-118).  fit() learns vocabulary (alphabetical == ascending
+    n-gram code) and idf; transform() emits the l2-normalised CSR in HBM."""
+
+    def __init__(self, n_gram_range=(3, 3), clean_string=True, remove_space_ngrams=True):
+        lo, hi = int(n_gram_range[0]), int(n_gram_range[1])
+        if not (1 <= lo <= hi <= 8):
+            raise ValueError(f"n_gram_range {n_gram_range} unsupported (1 <= lo <= hi <= 8)")
+        self.lo, self.hi = lo, hi
+        self.clean = bool(clean_string)
+        self.remove_space = bool(remove_space_ngrams)
+        self.flags = (FLAG_CLEAN if self.clean else 0) | (FLAG_REMOVE_SPACE if self.remove_space else 0)
+        self.base = CLEAN_BASE if self.clean else None
+        self.alphabet = None            # raw mode: sorted code points of the fit corpus (numpy uint32)
+        self.vocab_keys = None          # numpy uint64[V] ascending (host copy, for pickling / inspection)
+        self.idf = None                 # numpy float64[V]
+        self.df = None
+        self.n_fit_docs = 0
+        self._d_sym = self._d_vocab = self._d_idf = self._d_rank = None
+
+    # ---- pickling: device tensors are rebuilt lazily ---------------------------------------------
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in ("_d_sym", "_d_vocab", "_d_idf", "_d_rank"):
+            st[k] = None
+        return st
+
+    @property
+    def n_vocab(self):
+        return 0 if self.vocab_keys is None else len(self.vocab_keys)
+
+    def code_space(self):
+        return int(self.base) ** self.hi
+
+    def vocabulary(self):
+        """n-gram strings in column order (decoded from the codes) -- sklearn's sorted vocabulary_."""
+        out = []
+        if self.clean:
+            symbols = [None, " "] + [chr(c) for c in range(48, 58)] + [chr(c) for c in range(97, 123)]
+        else:
+            symbols = [None] + [chr(int(c)) for c in self.alphabet]
+        for key in self.vocab_keys.tolist():
+            digs = []
+            for _ in range(self.hi):
+                digs.append(key % self.base); key //= self.base
+            out.append("".join(symbols[d] for d in reversed(digs) if d))
+        return out
+
+    # ---- stage A ----------------------------------------------------------------------------------
+    def _stage_a(self, strings, d_sym):
+        blob, offsets = pack_utf32(strings)
+        slots, occ = ngram_slot_bounds(offsets, self.lo, self.hi)
+        if len(slots) and slots.max() > MAX_ROW_SLOTS:
+            r = int(slots.argmax())
+            raise ValueError(f"string {r} has {int(slots[r])} n-gram slots; the vectoriser supports at most "
+                             f"{MAX_ROW_SLOTS} per string")
+        long_rows = np.nonzero(slots > WARP_ROW_SLOTS)[0].astype(np.int32)
+        R = _Rows()
+        R.n = len(strings)
+        R.cap = int(occ[-1])
+        d_blob = _to_dev(blob.view(np.int32), torch.int32) if blob.size else torch.zeros(1, dtype=torch.int32, device=_dev())
+        d_off = _to_dev(offsets)
+        R.occ_ptr = _to_dev(occ)
+        d_long = _to_dev(long_rows) if len(long_rows) else None
+        R.codes = torch.empty(max(R.cap, 1), dtype=torch.int64, device=_dev())
+        R.tf = torch.empty(max(R.cap, 1), dtype=torch.int32, device=_dev())
+        R.row_cnt = torch.zeros(max(R.n, 1), dtype=torch.int32, device=_dev())
+        _lib.call("pfz_ngram_rows", _p(d_blob), _p(d_off), R.n, self.lo, self.hi, self.flags, _p(d_sym),
+                  int(self.base), _p(R.occ_ptr), _p(d_long), len(long_rows), _p(R.codes), _p(R.tf), _p(R.row_cnt),
+                  _stream())
+        R._keep = (d_blob, d_off, d_long)
+        return R
+
+    def _fit_alphabet(self, lists):
+        present = torch.zeros(N_CODE_POINTS, dtype=torch.uint8, device=_dev())
+        keep = []
+        for strings in lists:
+            blob, _ = pack_utf32(strings)
+            if blob.size:
+                d_blob = _to_dev(blob.view(np.int32), torch.int32); keep.append(d_blob)
+                _lib.call("pfz_alphabet_mark", _p(d_blob), int(blob.size), _p(present), _stream())
+        self.alphabet = np.nonzero(present.cpu().numpy())[0].astype(np.uint32)
+        self.base = len(self.alphabet) + 1
+
+    def _sym_table(self):
+        if self.clean:
+            return None
+        if self._d_sym is None:
+            tab = np.full(N_CODE_POINTS, 0xFFFFFFFF, dtype=np.uint32)
+            tab[self.alphabet] = np.arange(1, len(self.alphabet) + 1, dtype=np.uint32)
+            self._d_sym = _to_dev(tab.view(np.int32), torch.int32)
+        return self._d_sym
+
+    # ---- fit ----------------------------------------------------------------------------------------
+    def fit_rows(self, lists):
+        """lists: the fit corpus as 1 or 2 string lists (the reference fits on to_list + from_list,
+        _tfidf.py:109).  Returns the stage-A rows of each list so transform need not redo them."""
+        if not self.clean:
+            self._d_sym = None
+            self._fit_alphabet(lists)
+        if self.code_space() >= 2 ** 64:
+            raise ValueError(f"alphabet of {self.base - 1} symbols with {self.hi}-grams exceeds 64-bit n-gram codes")
+        d_sym = self._sym_table()
+        rows = [self._stage_a(s, d_sym) for s in lists]
+        n_docs = sum(r.n for r in rows)
+        dev = _dev()
+        d_nv = torch.zeros(1, dtype=torch.int32, device=dev)
+        cs = self.code_space()
+        total_cap = sum(r.cap for r in rows)
+        if total_cap == 0:
+            raise ValueError("empty vocabulary; perhaps the documents only contain stop words")
+        if cs <= DENSE_CODE_SPACE_MAX:
+            df_dense = torch.zeros(cs, dtype=torch.int32, device=dev)
+            for r in rows:
+                _lib.call("pfz_df_dense", _p(r.codes), _p(r.occ_ptr), _p(r.row_cnt), r.n, _p(df_dense), _stream())
+            vmax = min(cs, total_cap)
+            d_vocab = torch.empty(vmax, dtype=torch.int64, device=dev)
+            d_df = torch.empty(vmax, dtype=torch.int32, device=dev)
+            d_rank = torch.empty(cs, dtype=torch.int32, device=dev)
+            ws = _ws(_lib.load().pfz_scan_ws_bytes(cs))
+            _lib.call("pfz_vocab_compact_dense", _p(df_dense), cs, _p(d_vocab), _p(d_df), _p(d_rank), _p(d_nv), _p(ws), _stream())
+        else:
+            cap2 = 1 << max(int(total_cap - 1).bit_length(), 1)
+            keys = torch.full((cap2,), -1, dtype=torch.int64, device=dev)       # ~0 padding
+            cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+            for r in rows:
+                _lib.call("pfz_gather_codes", _p(r.codes), _p(r.occ_ptr), _p(r.row_cnt), r.n, _p(keys), _p(cursor), _stream())
+            _lib.call("pfz_sort_u64", _p(keys), cap2, _stream())
+            d_vocab = torch.empty(total_cap, dtype=torch.int64, device=dev)
+            d_df = torch.empty(total_cap, dtype=torch.int32, device=dev)
+            d_rank = None
+            ws = _ws(cap2 * 8 + 256 + _lib.load().pfz_scan_ws_bytes(cap2))
+            _lib.call("pfz_vocab_from_sorted", _p(keys), cap2, _p(cursor), _p(d_vocab), _p(d_df), _p(d_nv), _p(ws), _stream())
+        V = int(d_nv.item())                                  # the one host sync of fit
+        if V == 0:
+            raise ValueError("empty vocabulary; perhaps the documents only contain stop words")
+        self.vocab_keys = d_vocab[:V].cpu().numpy().view(np.uint64)
+        self.df = d_df[:V].cpu().numpy().astype(np.int64)
+        self.n_fit_docs = n_docs
+        # idf exactly as scikit-learn computes it on the host (sk:feature_extraction/text.py:1679-1694):
+        # np.log((n_samples + 1) / (df + 1)) + 1 -- same numpy, same bits as the reference on this machine.
+        self.idf = np.log((n_docs + 1.0) / (self.df.astype(np.float64) + 1.0)) + 1.0
+        self._d_vocab = d_vocab[:V]
+        self._d_rank = d_rank
+        self._d_idf = _to_dev(self.idf)
+        return rows
+
+    def _ensure_device_state(self):
+        if self.vocab_keys is None:
+            raise ValueError("vectoriser is not fitted")
+        if self._d_vocab is None:
+            self._d_vocab = _to_dev(self.vocab_keys.view(np.int64))
+            self._d_idf = _to_dev(self.idf)
+            self._d_rank = None
+            cs = self.code_space()
+            if cs <= DENSE_CODE_SPACE_MAX:
+                rank = np.full(cs, -1, dtype=np.int32)
+                rank[self.vocab_keys.astype(np.int64)] = np.arange(len(self.vocab_keys), dtype=np.int32)
+                self._d_rank = _to_dev(rank)
+
+    # ---- transform ----------------------------------------------------------------------------------
+    def rows(self, strings):
+        self._ensure_device_state()
+        return self._stage_a(strings, self._sym_table())
+
+    def emit(self, R):
+        self._ensure_device_state()
+        dev = _dev()
+        indptr = torch.empty(R.n + 1, dtype=torch.int32, device=dev)
+        indices = torch.empty(max(R.cap, 1), dtype=torch.int32, device=dev)
+        data = torch.empty(max(R.cap, 1), dtype=torch.float64, device=dev)
+        ws = _ws(_lib.load().pfz_scan_ws_bytes(R.n + 1))
+        _lib.call("pfz_tfidf_emit", _p(R.codes), _p(R.tf), _p(R.occ_ptr), _p(R.row_cnt), R.n, _p(self._d_rank),
+                  _p(self._d_vocab), self.n_vocab, _p(self._d_idf), _p(indptr), _p(indices), _p(data), _p(ws), _stream())
+        return CsrMatrix(indptr, indices, data, R.n, self.n_vocab)
+
+    def fit(self, strings):
+        self.fit_rows([strings])
+        return self
+
+    def transform(self, strings):
+        return self.emit(self.rows(strings))
+
+
+DEFAULT_TILE = int(os.environ.get("PFZ_TILE", "2048"))
+K2_WARPS = 8
+
+
+class SparseIndex:
+    """Inverted index of a to-matrix shard: postings grouped by (term, to-tile)."""
+
+    def __init__(self, csr: CsrMatrix, tile=None):
+        n = csr.n_rows
+        if tile is None:
+            tile = DEFAULT_TILE
+        tile = max(32, min(int(tile), ((max(n, 1) + 31) // 32) * 32))
+        self.tile = tile
+        self.n_to = n
+        self.n_vocab = csr.n_cols
+        self.n_tiles = max(1, (n + tile - 1) // tile)
+        ncell = self.n_vocab * self.n_tiles
+        dev = _dev()
+        self.seg = torch.empty(ncell + 1, dtype=torch.int32, device=dev)
+        cap = max(csr.indices.numel(), 1)
+        self.post_idx = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.post_val = torch.empty(cap, dtype=torch.float64, device=dev)
+        ws = _ws((ncell + 1) * 4 + 512 + _lib.load().pfz_scan_ws_bytes(ncell + 1))
+        _lib.call("pfz_index_build", _p(csr.indptr), _p(csr.indices), _p(csr.data), n, self.n_vocab, tile,
+                  self.n_tiles, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(ws), _stream())
+
+
+def _auto_splits(n_from, n_tiles, sm_count=148):
+    want = sm_count * K2_WARPS * 2
+    if n_from >= want:
+        return 1
+    return max(1, min(n_tiles, (want + max(n_from, 1) - 1) // max(n_from, 1)))
+
+
+def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_match=False, from_index_base=0,
+               to_index_base=0, n_splits=None):
+    """K2.  Returns (top_idx int32[n_from,k] GLOBAL to-indices or -1, top_val float64[n_from,k]) on device."""
+    dev = _dev()
+    n_from = a.n_rows
+    k = int(k)
+    if k < 1:
+        raise ValueError("top_n must be >= 1")
+    if n_splits is None:
+        n_splits = _auto_splits(n_from, index.n_tiles)
+    n_splits = max(1, min(int(n_splits), index.n_tiles))
+    counter = torch.zeros(n_splits, dtype=torch.int32, device=dev)
+    pages = []
+    excl_v = excl_i = None
+    remaining = k
+    while remaining > 0:
+        kp = min(32, remaining)
+        ti = torch.empty((n_splits, max(n_from, 1), kp), dtype=torch.int32, device=dev)
+        tv = torch.empty((n_splits, max(n_from, 1), kp), dtype=torch.float64, device=dev)
+        _lib.call("pfz_spcos_topk", _p(a.indptr), _p(a.indices), _p(a.data), n_from, _p(index.seg), _p(index.post_idx),
+                  _p(index.post_val), index.n_vocab, index.tile, index.n_tiles, index.n_to, kp, float(min_similarity),
+                  int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, _p(excl_v), _p(excl_i),
+                  _p(ti), _p(tv), _p(counter), _stream())
+        if n_splits > 1:
+            oi = torch.empty((max(n_from, 1), kp), dtype=torch.int32, device=dev)
+            ov = torch.empty((max(n_from, 1), kp), dtype=torch.float64, device=dev)
+            _lib.call("pfz_topk_merge", _p(ti), _p(tv), n_splits, n_from, kp, kp, _p(oi), _p(ov), _stream())
+        else:
+            oi, ov = ti[0], tv[0]
+        pages.append((oi, ov))
+        remaining -= kp
+        if remaining > 0:
+            excl_v = ov[:, -1].contiguous(); excl_i = oi[:, -1].contiguous()
+            # rows whose page is not full are exhausted: an idx of -1 disables the filter, so give them
+            # an unbeatable exclusive key instead (nothing ranks after (-inf, INT_MAX))
+            done = excl_i < 0
+            excl_v = torch.where(done, torch.full_like(excl_v, float("-inf")), excl_v)
+            excl_i = torch.where(done, torch.full_like(excl_i, 2 ** 31 - 1), excl_i)
+    if len(pages) == 1:
+        oi, ov = pages[0]
+    else:
+        oi = torch.cat([p[0] for p in pages], dim=1); ov = torch.cat([p[1] for p in pages], dim=1)
+    return oi[:n_from], ov[:n_from]
+
+
+def topk_merge(idx, val, k_out):
+    """Merge [n_lists, n_from, k_in] candidate lists into the canonical top-k_out (device tensors)."""
+    n_lists, n_from, k_in = idx.shape
+    dev = idx.device
+    oi = torch.empty((n_from, k_out), dtype=torch.int32, device=dev)
+    ov = torch.empty((n_from, k_out), dtype=torch.float64, device=dev)
+    _lib.call("pfz_topk_merge", _p(idx.contiguous()), _p(val.contiguous()), n_lists, n_from, k_in, k_out, _p(oi), _p(ov), _stream())
+    return oi, ov

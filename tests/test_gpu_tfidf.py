@@ -1,0 +1,224 @@
+"""GPU parity tests of K1 (vectoriser) and K2 (sparse cosine top-k) against the oracle and against
+the golden fixtures generated from the unmodified reference (tests/golden/make_golden.py).
+Bit-exact: CSR structure, CSR values, top-k indices and (unrounded) scores."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import native as onative
+from oracle import tfidf as otfidf
+from oracle.assemble import assemble as oracle_assemble
+
+pytestmark = pytest.mark.gpu
+
+FROM = ["apple", "apples", "appl", "recal", "house", "similarity"]
+TO = ["apple", "apples", "mouse"]
+RANGES = [(1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 3), (3, 6)]
+
+
+@pytest.fixture(scope="module")
+def pf():
+    import polyfuzz_b200
+    from polyfuzz_b200 import engine
+    return polyfuzz_b200, engine
+
+
+def _csr_eq(dev_csr, indptr, indices, data, shape):
+    m = dev_csr.to_scipy()
+    assert m.shape == tuple(shape)
+    np.testing.assert_array_equal(m.indptr, indptr)
+    np.testing.assert_array_equal(m.indices, indices)
+    np.testing.assert_array_equal(m.data, data)          # bit-exact fp64
+
+
+@pytest.mark.parametrize("lo,hi", RANGES)
+@pytest.mark.parametrize("clean", [True, False])
+@pytest.mark.parametrize("rs", [True, False])
+def test_c1_vectoriser_matches_reference(pf, golden_dir, lo, hi, clean, rs):
+    _, engine = pf
+    g = np.load(os.path.join(golden_dir, "c1_tfidf.npz"))
+    voc = json.load(open(os.path.join(golden_dir, "c1_vocab.json")))
+    tag = f"r{lo}{hi}_c{int(clean)}_s{int(rs)}"
+    v = engine.NgramTfidf((lo, hi), clean, rs)
+    rows_to, rows_from = v.fit_rows([TO, FROM])
+    assert v.vocabulary() == voc[tag + "_two"]
+    np.testing.assert_array_equal(v.idf, g[tag + "_two_idf"])
+    for name, rows in (("to", rows_to), ("from", rows_from)):
+        _csr_eq(v.emit(rows), g[f"{tag}_two_{name}_indptr"], g[f"{tag}_two_{name}_indices"], g[f"{tag}_two_{name}_data"],
+                g[f"{tag}_two_{name}_shape"])
+    v2 = engine.NgramTfidf((lo, hi), clean, rs)
+    (rows,) = v2.fit_rows([FROM])
+    assert v2.vocabulary() == voc[tag + "_self"]
+    _csr_eq(v2.emit(rows), g[tag + "_self_indptr"], g[tag + "_self_indices"], g[tag + "_self_data"], g[tag + "_self_shape"])
+
+
+def _frame_eq(df, ref):
+    assert list(df.columns) == list(ref.keys())
+    for c in df.columns:
+        got = [None if (isinstance(v, float) and np.isnan(v)) else v for v in df[c].tolist()]
+        assert got == ref[c], c
+
+
+@pytest.mark.parametrize("top_n", [1, 2, 3])
+@pytest.mark.parametrize("ms", [0.0, 0.75])
+def test_c1_match_frames_equal_reference(pf, golden_dir, top_n, ms):
+    polyfuzz_b200, _ = pf
+    ref = json.load(open(os.path.join(golden_dir, "c1_match.json")))
+    m = polyfuzz_b200.TFIDF(min_similarity=ms, top_n=top_n)
+    # the reference sklearn branch ignores min_similarity; compare where they agree: ms=0
+    if ms == 0.0:
+        _frame_eq(m.match(FROM, TO), ref[f"two_top{top_n}_ms{ms}"])
+        m = polyfuzz_b200.TFIDF(min_similarity=ms, top_n=top_n)
+        _frame_eq(m.match(FROM), ref[f"self_top{top_n}_ms{ms}"])
+    else:
+        df = m.match(FROM, TO)
+        r0 = ref[f"two_top{top_n}_ms0.0"]
+        # sparse-branch semantics: keep only scores > min_similarity
+        for c in [c for c in df.columns if c.startswith("Similarity")]:
+            exp = [v if v > ms else 0.0 for v in r0[c]]
+            assert df[c].tolist() == exp
+
+
+def test_c1_transform_path(pf, golden_dir):
+    polyfuzz_b200, _ = pf
+    ref = json.load(open(os.path.join(golden_dir, "c1_match.json")))["transform_unseen"]
+    m = polyfuzz_b200.TFIDF(min_similarity=0, top_n=1)
+    m.match(FROM, TO)
+    _frame_eq(m.match(["apples", "mouses", "zzz"], TO, re_train=False), ref)
+
+
+@pytest.fixture(scope="module")
+def company(golden_dir):
+    g = np.load(os.path.join(golden_dir, "company_slice.npz"))
+    names = json.load(open(os.path.join(golden_dir, "company_slice_names.json")))["names"]
+    return g, names
+
+
+def test_company_slice_vectoriser_bit_exact(pf, company):
+    _, engine = pf
+    g, names = company
+    v = engine.NgramTfidf((3, 3), True, True)
+    (rows,) = v.fit_rows([names])
+    np.testing.assert_array_equal(v.idf, g["idf"])
+    _csr_eq(v.emit(rows), g["csr_indptr"], g["csr_indices"], g["csr_data"], g["csr_shape"])
+
+
+@pytest.mark.parametrize("tile", [None, 256, 1024])
+@pytest.mark.parametrize("n_splits", [1, 3])
+def test_company_slice_topk_vs_oracle_and_reference(pf, company, tile, n_splits):
+    polyfuzz_b200, engine = pf
+    g, names = company
+    k = 10
+    v = engine.NgramTfidf((3, 3), True, True)
+    (rows,) = v.fit_rows([names])
+    csr = v.emit(rows)
+    index = engine.SparseIndex(csr, tile=tile)
+    idx, val = engine.spcos_topk(csr, index, k, 0.0, self_match=True, n_splits=n_splits)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    a = csr.to_scipy()
+    oi, ov = onative.spdot_topn(a, a, k, 0.0, self_match=True)
+    np.testing.assert_array_equal(idx, oi)               # canonical contract: bit-exact indices
+    np.testing.assert_array_equal(val, ov)               # and bit-exact fp64 scores
+    # unmodified reference (sklearn branch): all 3-dp scores equal; indices equal on tie-free rows
+    np.testing.assert_array_equal(np.round(val, 3), g["ref_sims"])
+    tf = g["ref_tiefree"]
+    nz = g["ref_topvals"] > 0
+    same = (idx == g["ref_idx"]) | ~nz
+    assert same[tf].all()
+
+
+def test_company_slice_match_frame(pf, company):
+    polyfuzz_b200, engine = pf
+    g, names = company
+    m = polyfuzz_b200.TFIDF(min_similarity=0, top_n=10)
+    df = m.match(names)
+    a = m.tf_idf_to.to_scipy()
+    oi, ov = onative.spdot_topn(a, a, 10, 0.0, self_match=True)
+    exp = oracle_assemble(names, None, oi, ov)
+    assert list(df.columns) == list(exp.columns)
+    for c in df.columns:
+        if c.startswith("Similarity"):
+            np.testing.assert_array_equal(df[c].to_numpy(), exp[c].to_numpy())
+        else:
+            assert [None if (isinstance(v, float) and np.isnan(v)) else v for v in df[c].tolist()] == \
+                   [None if (isinstance(v, float) and np.isnan(v)) else v for v in exp[c].tolist()]
+
+
+def _oracle_two(frm, to, rng=(3, 3), clean=True, rs=True):
+    f, t, _ = otfidf.fit_transform_sklearn(frm, to, rng, clean, rs)
+    return f, t
+
+
+@pytest.mark.parametrize("k,ms", [(1, 0.0), (5, 0.3), (32, 0.0), (40, 0.0), (70, 0.05)])
+def test_synthetic_two_list_vs_oracle(pf, k, ms):
+    polyfuzz_b200, engine = pf
+    from polyfuzz_b200 import synth
+    to = synth.company_names(6000, seed=3)
+    frm = synth.company_names(2500, seed=4) + ["", "a", "ab", "  ", "!!!", to[17], to[17].lower()]
+    m = polyfuzz_b200.TFIDF(min_similarity=ms, top_n=k)
+    idx, val, kk = m.match_arrays(frm, to)
+    f, t = _oracle_two(frm, to)
+    np.testing.assert_array_equal(m.tf_idf_to.to_scipy().data, t.data)
+    oi, ov = onative.spdot_topn(f, t, kk, ms)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(val.cpu().numpy(), ov)
+
+
+def test_uniform_strings_vs_oracle(pf):
+    """BASELINE config 5 shape (uniform 8..32 chars over 37 symbols) at an oracle-sized scale."""
+    polyfuzz_b200, engine = pf
+    from polyfuzz_b200 import synth
+    to = synth.uniform_strings(20000, seed=0)
+    frm = synth.uniform_strings(5000, seed=1)
+    m = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=10)
+    idx, val, kk = m.match_arrays(frm, to)
+    f, t = _oracle_two(frm, to)
+    oi, ov = onative.spdot_topn(f, t, kk, 0.0, n_threads=8)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(val.cpu().numpy(), ov)
+
+
+def test_edge_cases(pf):
+    polyfuzz_b200, engine = pf
+    # long strings (> 256 n-gram slots -> long-row kernel), duplicates, unicode survivors, whitespace
+    long_a = "alpha beta gamma delta " * 30
+    long_b = "alpha beta gamma delta " * 29 + "epsilon"
+    frm = [long_a, "İstanbul Kelvin K", "x\ty\nz  w", "dup", "dup", "", "ab"]
+    to = [long_b, "istanbul kelvin k", "xyz w", "dup", "other", "dup"]
+    for rng in [(3, 3), (2, 4), (1, 1)]:
+        for clean in (True, False):
+            m = polyfuzz_b200.TFIDF(n_gram_range=rng, clean_string=clean, min_similarity=0.0, top_n=3)
+            idx, val, kk = m.match_arrays(frm, to)
+            f, t = _oracle_two(frm, to, rng, clean, True)
+            got = m.tf_idf_to.to_scipy()
+            np.testing.assert_array_equal(got.indices, t.indices)
+            np.testing.assert_array_equal(got.data, t.data)
+            oi, ov = onative.spdot_topn(f, t, kk, 0.0)
+            np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+            np.testing.assert_array_equal(val.cpu().numpy(), ov)
+    # self-match excludes only the diagonal: duplicates at other positions still match with 1.0
+    m = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=1)
+    df = m.match(["dup", "dup", "zzz"])
+    assert df["To"].tolist()[:2] == ["dup", "dup"] and df["Similarity"].tolist()[:2] == [1.0, 1.0]
+    assert df["To"].tolist()[2] is None or df["To"].isna().tolist()[2]
+    # top_n is clipped to the number of distinct to-strings (_utils.py:54-56)
+    m = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=10)
+    assert list(m.match(FROM, TO).columns) == ["From", "To", "Similarity", "To_2", "Similarity_2", "To_3", "Similarity_3"]
+    # empty vocabulary raises like scikit-learn
+    with pytest.raises(ValueError, match="empty vocabulary"):
+        polyfuzz_b200.TFIDF().match(["a", "b"], ["c"])
+
+
+def test_pickle_round_trip(pf, tmp_path):
+    import joblib
+    polyfuzz_b200, _ = pf
+    m = polyfuzz_b200.TFIDF(min_similarity=0, top_n=1)
+    m.match(FROM, TO)
+    exp = m.match(["appl", "mouses"], TO, re_train=False)
+    joblib.dump(m, tmp_path / "m.joblib")
+    m2 = joblib.load(tmp_path / "m.joblib")
+    got = m2.match(["appl", "mouses"], TO, re_train=False)
+    assert got.equals(exp)
