@@ -75,7 +75,7 @@ class CsrMatrix:
 
 class _Rows:
     """Stage-A result for one string list: per-row sorted distinct n-gram codes + counts."""
-    __slots__ = ("n", "occ_ptr", "codes", "tf", "row_cnt", "cap")
+    __slots__ = ("n", "occ_ptr", "codes", "tf", "row_cnt", "cap", "_keep")
 
 
 class NgramTfidf:

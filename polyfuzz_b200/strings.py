@@ -14,7 +14,7 @@ def pack_utf32(strings):
         raw = "".join(strings).encode("utf-32-le", "surrogatepass")
     except TypeError as e:                       # non-str element
         raise TypeError("all elements of the string list must be str") from e
-    blob = np.frombuffer(raw, dtype=np.uint32)
+    blob = np.frombuffer(raw, dtype=np.uint32).copy()       # writable (torch.from_numpy)
     if blob.size != offsets[-1]:
         raise ValueError("string list could not be packed as UTF-32")
     return blob, offsets
