@@ -38,6 +38,8 @@ extern "C" {
 
 int         pfz_abi_version(void);
 const char *pfz_last_error(void);
+/* number of CUDA kernels this library has launched in this process (monotonic) */
+int64_t     pfz_launch_count(void);
 /* device properties the host code needs for launch sizing: sm_count, max dynamic smem per block */
 int pfz_device_info(int32_t *sm_count, int32_t *smem_per_block_optin, int32_t *cc_major, int32_t *cc_minor);
 

@@ -29,21 +29,32 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+class InvertedIndex:
+    """to-matrix transposed to term-major posting lists (what awesome_cossim_topn receives as B)."""
+
+    def __init__(self, b_csr):
+        import scipy.sparse as sp
+        bt = sp.csr_matrix(b_csr).T.tocsr(); bt.sort_indices()       # docs ascending inside each term
+        self.n_to = b_csr.shape[0]
+        self.indptr = np.ascontiguousarray(bt.indptr, dtype=np.int32)
+        self.indices = np.ascontiguousarray(bt.indices, dtype=np.int32)
+        self.data = np.ascontiguousarray(bt.data, dtype=np.float64)
+
+
 def spdot_topn(a_csr, b_csr, k, lower_bound=0.0, self_match=False, from_index_base=0,
                to_index_base=0, n_threads=1):
     """Gustavson sparse dot + canonical top-k (restates awesome_cossim_topn at _utils.py:82 plus
-    the post-processing at _utils.py:84-91,128-146).  a_csr: from (n_from x V), b_csr: to (n_to x V)."""
+    the post-processing at _utils.py:84-91,128-146).  a_csr: from (n_from x V); b_csr: to (n_to x V)
+    or a prebuilt InvertedIndex."""
     import scipy.sparse as sp
     a = sp.csr_matrix(a_csr); a.sort_indices()
-    bt = sp.csr_matrix(b_csr).T.tocsr(); bt.sort_indices()       # inverted index, docs ascending
-    n_from, n_to = a.shape[0], b_csr.shape[0]
+    bt = b_csr if isinstance(b_csr, InvertedIndex) else InvertedIndex(b_csr)
+    n_from, n_to = a.shape[0], bt.n_to
     ai = np.ascontiguousarray(a.indptr, dtype=np.int32); aj = np.ascontiguousarray(a.indices, dtype=np.int32)
     av = np.ascontiguousarray(a.data, dtype=np.float64)
-    bi = np.ascontiguousarray(bt.indptr, dtype=np.int32); bj = np.ascontiguousarray(bt.indices, dtype=np.int32)
-    bv = np.ascontiguousarray(bt.data, dtype=np.float64)
     idx = np.empty((n_from, k), dtype=np.int32); val = np.empty((n_from, k), dtype=np.float64)
     rc = lib().oracle_spdot_topn(ctypes.c_int32(n_from), ctypes.c_int32(n_to), _p(ai), _p(aj), _p(av),
-                                 _p(bi), _p(bj), _p(bv), ctypes.c_int32(k), ctypes.c_double(lower_bound),
+                                 _p(bt.indptr), _p(bt.indices), _p(bt.data), ctypes.c_int32(k), ctypes.c_double(lower_bound),
                                  ctypes.c_int32(int(self_match)), ctypes.c_int64(from_index_base),
                                  ctypes.c_int64(to_index_base), _p(idx), _p(val), ctypes.c_int32(n_threads))
     if rc:

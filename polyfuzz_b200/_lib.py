@@ -13,6 +13,7 @@ c_i32, c_i64, c_u32, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint
 _PROTOS = {
     "pfz_abi_version": [],
     "pfz_last_error": [],
+    "pfz_launch_count": [],
     "pfz_device_info": [c_vp, c_vp, c_vp, c_vp],
     "pfz_scan_ws_bytes": [c_i64],
     "pfz_alphabet_mark": [c_vp, c_i64, c_vp, c_vp],
@@ -28,7 +29,7 @@ _PROTOS = {
                        c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pfz_topk_merge": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp],
 }
-_RESTYPES = {"pfz_last_error": ctypes.c_char_p, "pfz_scan_ws_bytes": c_i64}
+_RESTYPES = {"pfz_last_error": ctypes.c_char_p, "pfz_scan_ws_bytes": c_i64, "pfz_launch_count": c_i64}
 
 
 def exported_names():
@@ -62,3 +63,7 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed: {lib.pfz_last_error().decode(errors='replace')}")
+
+
+def launch_count():
+    return int(load().pfz_launch_count())

@@ -19,7 +19,9 @@ void set_error(const char *fmt, ...);
         }                                                                                   \
     } while (0)
 
-#define PFZ_LAUNCH_OK()  PFZ_CUDA_OK(cudaGetLastError())
+extern unsigned long long g_launches;   // kernels launched by this library (bench.py reports it)
+#define PFZ_LAUNCH_OK()                                                                     \
+    do { __atomic_fetch_add(&pfz::g_launches, 1ull, __ATOMIC_RELAXED); PFZ_CUDA_OK(cudaGetLastError()); } while (0)
 
 #define PFZ_REQUIRE(cond, ...)                                                              \
     do {                                                                                    \

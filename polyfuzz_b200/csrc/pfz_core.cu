@@ -4,6 +4,7 @@
 
 namespace pfz {
 static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;
 void set_error(const char *fmt, ...) {
     va_list ap; va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -81,6 +82,7 @@ extern "C" {
 
 int pfz_abi_version(void) { return PFZ_ABI_VERSION; }
 const char *pfz_last_error(void) { return pfz::g_err; }
+int64_t pfz_launch_count(void) { return (int64_t)__atomic_load_n(&pfz::g_launches, __ATOMIC_RELAXED); }
 
 int64_t pfz_scan_ws_bytes(int64_t n) {
     int64_t total = 256;

@@ -1,0 +1,104 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), `torch.distributed` over NCCL/NVLink.
+
+The path shards by to_list row-blocks: rank r owns to-rows
+[r*ceil(n_to/G), ...), builds its own inverted index, scores every from-row against its shard with
+GLOBAL to-indices, and the per-shard top-k lists are exchanged with ONE all-gather
+(n_from * k * 16 B per rank) followed by the pfz_topk_merge kernel with the same
+(score desc, index asc) key -- so the result is bit-identical to the single-GPU result.
+The TF-IDF fit needs the global document frequencies: one all-reduce(SUM) of the dense int32 df table.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_total, world_size, rank):
+    """Contiguous row-block of rank: [lo, hi)."""
+    per = (n_total + world_size - 1) // world_size if world_size > 0 else n_total
+    lo = min(n_total, rank * per)
+    return lo, min(n_total, lo + per)
+
+
+def pack_topk(idx, val):
+    """(int32[n,k], float64[n,k]) -> int64[n,k,2] so that one all-gather moves both."""
+    buf = torch.empty(idx.shape + (2,), dtype=torch.int64, device=idx.device)
+    buf[..., 0] = val.contiguous().view(torch.int64)
+    buf[..., 1] = idx.to(torch.int64)
+    return buf
+
+
+def unpack_topk(buf):
+    val = buf[..., 0].contiguous().view(torch.float64)
+    idx = buf[..., 1].to(torch.int32).contiguous()
+    return idx, val
+
+
+class Comm:
+    """Thin wrapper over a torch.distributed process group (nccl on GPUs, gloo in CPU tests)."""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+
+    def all_reduce_sum(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_max(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_gather_topk(self, idx, val):
+        """-> (idx int32[G,n,k], val float64[G,n,k]); ONE collective."""
+        local = pack_topk(idx, val)
+        n = local.shape[0]
+        out = torch.empty((self.world_size * n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=self.group)        # concatenated along dim 0
+        return unpack_topk(out.view((self.world_size, n) + tuple(local.shape[1:])))
+
+
+def get_comm(group=None):
+    """Comm for the default group, or None when not running distributed (world size 1)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return Comm(group)
+    return None
+
+
+def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, top_n, min_similarity,
+                       self_match, from_index_base=0, fit=True, fit_on_from=True, comm=None, index=None,
+                       tile=None, timings=None):
+    """Sharded TF-IDF top-k.  Every rank passes the same from-list and its own to-shard.
+    Returns (top_idx[n_from,k] GLOBAL indices, top_val[n_from,k], csr_to_shard, index)."""
+    from . import engine
+    if top_n > 32 and comm is not None:
+        raise NotImplementedError("multi-GPU top_n > 32 is not supported yet")
+    if fit:
+        counted = [True, fit_on_from and (comm is None or comm.rank == 0)]
+        staged = [staged_to_shard, staged_from]
+        same = staged_from is staged_to_shard           # single-GPU self-match: one matrix for both sides
+        if same:                                        # (polyfuzz/models/_tfidf.py:114-116)
+            (rows_to,) = vectorizer.fit_staged([staged_to_shard], comm=comm)
+            rows_from = rows_to
+        else:
+            rows_to, rows_from = vectorizer.fit_staged(staged, counted=counted, comm=comm)
+        csr_to = vectorizer.emit(rows_to)
+        index = engine.SparseIndex(csr_to, tile=tile)
+        csr_from = csr_to if same else vectorizer.emit(rows_from)
+    else:
+        csr_to = None
+        csr_from = vectorizer.emit(vectorizer.rows(staged_from))
+    ev = None
+    if timings is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    idx, val = engine.spcos_topk(csr_from, index, top_n, min_similarity, self_match=self_match,
+                                 from_index_base=from_index_base, to_index_base=to_index_base)
+    if ev is not None:
+        ev[1].record()
+        timings.append(ev)
+    if comm is not None:
+        gi, gv = comm.all_gather_topk(idx, val)
+        idx, val = engine.topk_merge(gi, gv, top_n)
+    return idx, val, csr_to, index

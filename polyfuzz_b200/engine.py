@@ -39,12 +39,13 @@ def _p(t):
 
 def _to_dev(arr, dtype=None):
     """numpy -> device tensor via pinned staging (async H2D on the current stream)."""
+    dev = _dev()                                           # fail loudly without a GPU, before any work
     t = torch.from_numpy(np.ascontiguousarray(arr))
     if dtype is not None:
         t = t.view(dtype)
     if t.numel() == 0:
-        return torch.empty(0, dtype=t.dtype, device=_dev())
-    return t.pin_memory().to(_dev(), non_blocking=True)
+        return torch.empty(0, dtype=t.dtype, device=dev)
+    return t.pin_memory().to(dev, non_blocking=True)
 
 
 def _ws(nbytes):
@@ -71,6 +72,31 @@ class CsrMatrix:
         m = m.tocsr(); m.sort_indices()
         return CsrMatrix(_to_dev(m.indptr.astype(np.int32)), _to_dev(m.indices.astype(np.int32)),
                          _to_dev(m.data.astype(np.float64)), m.shape[0], m.shape[1])
+
+
+class StagedStrings:
+    """One string list packed and resident in HBM (UTF-32 blob, offsets, n-gram slot prefix)."""
+    __slots__ = ("n", "n_chars", "d_blob", "d_off", "occ_ptr", "d_long", "n_long", "cap", "h2d_bytes", "lo", "hi")
+
+
+def stage_strings(strings, lo, hi):
+    """Host marshalling + H2D of one list (the only per-string Python work on the path)."""
+    blob, offsets = pack_utf32(strings)
+    slots, occ = ngram_slot_bounds(offsets, lo, hi)
+    if len(slots) and slots.max() > MAX_ROW_SLOTS:
+        r = int(slots.argmax())
+        raise ValueError(f"string {r} has {int(slots[r])} n-gram slots; the vectoriser supports at most "
+                         f"{MAX_ROW_SLOTS} per string")
+    long_rows = np.nonzero(slots > WARP_ROW_SLOTS)[0].astype(np.int32)
+    S = StagedStrings()
+    S.n, S.n_chars, S.cap, S.lo, S.hi = len(strings), int(blob.size), int(occ[-1]), lo, hi
+    S.d_blob = _to_dev(blob.view(np.int32), torch.int32) if blob.size else torch.zeros(1, dtype=torch.int32, device=_dev())
+    S.d_off = _to_dev(offsets)
+    S.occ_ptr = _to_dev(occ)
+    S.n_long = len(long_rows)
+    S.d_long = _to_dev(long_rows) if S.n_long else None
+    S.h2d_bytes = blob.nbytes + offsets.nbytes + occ.nbytes + long_rows.nbytes
+    return S
 
 
 class _Rows:
@@ -127,39 +153,29 @@ class NgramTfidf:
             out.append("".join(symbols[d] for d in reversed(digs) if d))
         return out
 
+    def stage(self, strings):
+        return stage_strings(strings, self.lo, self.hi)
+
     # ---- stage A ----------------------------------------------------------------------------------
-    def _stage_a(self, strings, d_sym):
-        blob, offsets = pack_utf32(strings)
-        slots, occ = ngram_slot_bounds(offsets, self.lo, self.hi)
-        if len(slots) and slots.max() > MAX_ROW_SLOTS:
-            r = int(slots.argmax())
-            raise ValueError(f"string {r} has {int(slots[r])} n-gram slots; the vectoriser supports at most "
-                             f"{MAX_ROW_SLOTS} per string")
-        long_rows = np.nonzero(slots > WARP_ROW_SLOTS)[0].astype(np.int32)
+    def _stage_a(self, S, d_sym):
         R = _Rows()
-        R.n = len(strings)
-        R.cap = int(occ[-1])
-        d_blob = _to_dev(blob.view(np.int32), torch.int32) if blob.size else torch.zeros(1, dtype=torch.int32, device=_dev())
-        d_off = _to_dev(offsets)
-        R.occ_ptr = _to_dev(occ)
-        d_long = _to_dev(long_rows) if len(long_rows) else None
+        R.n, R.cap, R.occ_ptr = S.n, S.cap, S.occ_ptr
         R.codes = torch.empty(max(R.cap, 1), dtype=torch.int64, device=_dev())
         R.tf = torch.empty(max(R.cap, 1), dtype=torch.int32, device=_dev())
         R.row_cnt = torch.zeros(max(R.n, 1), dtype=torch.int32, device=_dev())
-        _lib.call("pfz_ngram_rows", _p(d_blob), _p(d_off), R.n, self.lo, self.hi, self.flags, _p(d_sym),
-                  int(self.base), _p(R.occ_ptr), _p(d_long), len(long_rows), _p(R.codes), _p(R.tf), _p(R.row_cnt),
+        _lib.call("pfz_ngram_rows", _p(S.d_blob), _p(S.d_off), R.n, self.lo, self.hi, self.flags, _p(d_sym),
+                  int(self.base), _p(R.occ_ptr), _p(S.d_long), S.n_long, _p(R.codes), _p(R.tf), _p(R.row_cnt),
                   _stream())
-        R._keep = (d_blob, d_off, d_long)
+        R._keep = S
         return R
 
-    def _fit_alphabet(self, lists):
+    def _fit_alphabet(self, staged, comm=None):
         present = torch.zeros(N_CODE_POINTS, dtype=torch.uint8, device=_dev())
-        keep = []
-        for strings in lists:
-            blob, _ = pack_utf32(strings)
-            if blob.size:
-                d_blob = _to_dev(blob.view(np.int32), torch.int32); keep.append(d_blob)
-                _lib.call("pfz_alphabet_mark", _p(d_blob), int(blob.size), _p(present), _stream())
+        for S in staged:
+            if S.n_chars:
+                _lib.call("pfz_alphabet_mark", _p(S.d_blob), S.n_chars, _p(present), _stream())
+        if comm is not None:
+            comm.all_reduce_max(present)
         self.alphabet = np.nonzero(present.cpu().numpy())[0].astype(np.uint32)
         self.base = len(self.alphabet) + 1
 
@@ -176,25 +192,45 @@ class NgramTfidf:
     def fit_rows(self, lists):
         """lists: the fit corpus as 1 or 2 string lists (the reference fits on to_list + from_list,
         _tfidf.py:109).  Returns the stage-A rows of each list so transform need not redo them."""
+        return self.fit_staged([self.stage(l) for l in lists])
+
+    def fit_staged(self, staged, counted=None, comm=None):
+        """Fit on device-resident lists.  Multi-GPU (comm given): `counted[i]` says whether list i
+        contributes to df / n_docs on THIS rank (a replicated list is counted on rank 0 only); the
+        dense df table and the document count are summed across ranks (one all-reduce), after which
+        every rank derives the identical vocabulary and idf."""
+        if counted is None:
+            counted = [True] * len(staged)
         if not self.clean:
             self._d_sym = None
-            self._fit_alphabet(lists)
+            self._fit_alphabet(staged, comm)
         if self.code_space() >= 2 ** 64:
             raise ValueError(f"alphabet of {self.base - 1} symbols with {self.hi}-grams exceeds 64-bit n-gram codes")
         d_sym = self._sym_table()
-        rows = [self._stage_a(s, d_sym) for s in lists]
-        n_docs = sum(r.n for r in rows)
+        rows = [self._stage_a(S, d_sym) for S in staged]
+        n_docs = sum(r.n for r, c in zip(rows, counted) if c)
         dev = _dev()
         d_nv = torch.zeros(1, dtype=torch.int32, device=dev)
         cs = self.code_space()
         total_cap = sum(r.cap for r in rows)
-        if total_cap == 0:
+        if comm is not None:
+            if cs > DENSE_CODE_SPACE_MAX:
+                raise NotImplementedError("multi-GPU fit needs an n-gram code space <= 2^24 (e.g. cleaned n <= 4)")
+            meta = torch.tensor([n_docs, total_cap], dtype=torch.int64, device=dev)
+            comm.all_reduce_sum(meta)
+            n_docs, total_cap_all = int(meta[0].item()), int(meta[1].item())
+        else:
+            total_cap_all = total_cap
+        if total_cap_all == 0:
             raise ValueError("empty vocabulary; perhaps the documents only contain stop words")
         if cs <= DENSE_CODE_SPACE_MAX:
             df_dense = torch.zeros(cs, dtype=torch.int32, device=dev)
-            for r in rows:
-                _lib.call("pfz_df_dense", _p(r.codes), _p(r.occ_ptr), _p(r.row_cnt), r.n, _p(df_dense), _stream())
-            vmax = min(cs, total_cap)
+            for r, c in zip(rows, counted):
+                if c:
+                    _lib.call("pfz_df_dense", _p(r.codes), _p(r.occ_ptr), _p(r.row_cnt), r.n, _p(df_dense), _stream())
+            if comm is not None:
+                comm.all_reduce_sum(df_dense)
+            vmax = min(cs, total_cap_all)
             d_vocab = torch.empty(vmax, dtype=torch.int64, device=dev)
             d_df = torch.empty(vmax, dtype=torch.int32, device=dev)
             d_rank = torch.empty(cs, dtype=torch.int32, device=dev)
@@ -242,7 +278,7 @@ class NgramTfidf:
     # ---- transform ----------------------------------------------------------------------------------
     def rows(self, strings):
         self._ensure_device_state()
-        return self._stage_a(strings, self._sym_table())
+        return self._stage_a(strings if isinstance(strings, StagedStrings) else self.stage(strings), self._sym_table())
 
     def emit(self, R):
         self._ensure_device_state()

@@ -8,6 +8,7 @@ import pandas as pd
 from ._base import BaseMatcher
 from ._utils import assemble_matches, clip_top_n
 from .. import engine
+from ..distributed import get_comm, shard_bounds, tfidf_topk_sharded
 
 
 class TFIDF(BaseMatcher):
@@ -24,6 +25,10 @@ class TFIDF(BaseMatcher):
                        (candidates need score > min_similarity, polyfuzz/models/_utils.py:82).
         model_id: The name of the particular instance, used when comparing models
         remove_space_ngrams: Remove n-grams that contain a space
+        distributed: (new) when True and torch.distributed is initialised with world size > 1
+                     (torchrun, one process per GPU), every rank calls match() with the SAME lists;
+                     the to_list is sharded in contiguous row-blocks, per-shard top-k lists are
+                     exchanged with one NCCL all-gather and merged; all ranks return the same frame.
     """
 
     def __init__(self,
@@ -33,7 +38,8 @@ class TFIDF(BaseMatcher):
                  top_n: int = 1,
                  cosine_method: str = "sparse",
                  model_id: str = None,
-                 remove_space_ngrams=True):
+                 remove_space_ngrams=True,
+                 distributed: bool = False):
         super().__init__(model_id)
         self.type = "TF-IDF"
         self.n_gram_range = n_gram_range
@@ -44,7 +50,9 @@ class TFIDF(BaseMatcher):
         self.vectorizer = None
         self.tf_idf_to = None
         self.remove_space_ngrams = remove_space_ngrams
+        self.distributed = distributed
         self._index = None              # device inverted index of tf_idf_to (rebuilt lazily after unpickling)
+        self._shard = (0, 0)            # distributed: [lo, hi) to-rows owned by this rank
 
     def __getstate__(self):
         st = dict(self.__dict__)
@@ -53,18 +61,41 @@ class TFIDF(BaseMatcher):
             st["tf_idf_to"] = self.tf_idf_to.to_scipy()          # device CSR -> host scipy for joblib.dump
         return st
 
-    def match(self, from_list: List[str], to_list: List[str] = None, re_train: bool = True) -> pd.DataFrame:
+    def match(self, from_list: List[str], to_list: List[str] = None, re_train: bool = True,
+              from_block: Tuple[int, int] = None) -> pd.DataFrame:
         """Match two lists of strings to each other and return the most similar strings
-        (polyfuzz/models/_tfidf.py:68-100)."""
-        top_idx, top_val, top_n = self.match_arrays(from_list, to_list, re_train)
-        return assemble_matches(from_list, to_list, top_idx.cpu().numpy(), top_val.cpu().numpy())
+        (polyfuzz/models/_tfidf.py:68-100).
 
-    def match_arrays(self, from_list, to_list=None, re_train=True):
+        from_block=(lo, hi) (new, self-match only): return the matches of from_list[lo:hi] against the
+        whole from_list (diagonal excluded) -- one row-block of a self-match that is too large for one
+        call / one GPU; the frame has hi-lo rows."""
+        top_idx, top_val, top_n = self.match_arrays(from_list, to_list, re_train, from_block)
+        rows = from_list if from_block is None else from_list[from_block[0]:from_block[1]]
+        return assemble_matches(rows, to_list if to_list is not None else from_list,
+                                top_idx.cpu().numpy(), top_val.cpu().numpy())
+
+    def match_arrays(self, from_list, to_list=None, re_train=True, from_block=None):
         """Device-side result: (top_idx int32[n,k] with -1 for no match, top_val float64[n,k], k)."""
-        tf_idf_from, tf_idf_to = self._extract_tf_idf(from_list, to_list, re_train)
         top_n = clip_top_n(self.top_n, to_list)
         if top_n < 1:
             raise ValueError("top_n must be >= 1 and to_list must not be empty")
+        if from_block is not None:
+            if to_list is not None:
+                raise ValueError("from_block is only meaningful for a self-match (to_list=None)")
+            lo, hi = int(from_block[0]), int(from_block[1])
+            if not (0 <= lo <= hi <= len(from_list)):
+                raise ValueError(f"from_block {from_block} out of range")
+        comm = get_comm() if self.distributed else None
+        if comm is not None:
+            return self._match_sharded(comm, from_list, to_list, re_train, top_n, from_block) + (top_n,)
+        if from_block is not None:
+            # fit / index on the whole list, score only the block's rows (global diagonal excluded)
+            self._extract_tf_idf(from_list, None, re_train)
+            block = self.vectorizer.transform(from_list[lo:hi])
+            idx, val = engine.spcos_topk(block, self._index, top_n, self.min_similarity, self_match=True,
+                                         from_index_base=lo)
+            return idx, val, top_n
+        tf_idf_from, tf_idf_to = self._extract_tf_idf(from_list, to_list, re_train)
         idx, val = engine.spcos_topk(tf_idf_from, self._index, top_n, self.min_similarity,
                                      self_match=to_list is None)
         return idx, val, top_n
@@ -94,6 +125,33 @@ class TFIDF(BaseMatcher):
         if self._index is None:
             self._index = engine.SparseIndex(self._device_to())
         return tf_idf_from, self.tf_idf_to
+
+    def _match_sharded(self, comm, from_list, to_list, re_train, top_n, from_block=None):
+        if re_train:
+            self.vectorizer = engine.NgramTfidf(self.n_gram_range, self.clean_string, self.remove_space_ngrams)
+        elif self.vectorizer is None or self._index is None:
+            raise ValueError("re_train=False needs a fitted model (call match/fit first)")
+        vec = self.vectorizer
+        self_match = to_list is None
+        full_to = to_list if to_list else from_list          # `if to_list:` as in _tfidf.py:107
+        from_base = 0
+        if from_block is not None:
+            from_base = int(from_block[0])
+            from_list = from_list[from_block[0]:from_block[1]]
+        staged_from = vec.stage(from_list)
+        if re_train:
+            lo, hi = shard_bounds(len(full_to), comm.world_size, comm.rank)
+            self._shard = (lo, hi)
+            staged_to = vec.stage(full_to[lo:hi])
+        else:
+            lo, hi = self._shard
+            staged_to = None
+        idx, val, csr_to, index = tfidf_topk_sharded(vec, staged_from, staged_to, lo, top_n, self.min_similarity,
+                                                     self_match, from_base, fit=re_train, fit_on_from=bool(to_list), comm=comm,
+                                                     index=self._index)
+        if re_train:
+            self.tf_idf_to, self._index = csr_to, index
+        return idx, val
 
     def _device_to(self):
         if hasattr(self.tf_idf_to, "tocsr"):                      # restored from a pickle

@@ -222,3 +222,12 @@ def test_pickle_round_trip(pf, tmp_path):
     m2 = joblib.load(tmp_path / "m.joblib")
     got = m2.match(["appl", "mouses"], TO, re_train=False)
     assert got.equals(exp)
+
+
+def test_from_block_is_a_row_block_of_the_self_match(pf):
+    polyfuzz_b200, engine = pf
+    from polyfuzz_b200 import synth
+    names = synth.company_names(3000, seed=9)
+    full = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=4).match(names)
+    blk = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=4).match(names, from_block=(1000, 1800))
+    assert blk.reset_index(drop=True).equals(full.iloc[1000:1800].reset_index(drop=True))

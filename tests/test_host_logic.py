@@ -1,0 +1,96 @@
+"""CPU tests of the host side: string packing, slot bounds, frame assembly, the C-ABI library
+(loads, exports every symbol include/pfz.h declares), plugin contract, loud failure without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import polyfuzz_b200
+from polyfuzz_b200 import _lib
+from polyfuzz_b200.strings import pack_utf32, ngram_slot_bounds
+from polyfuzz_b200.matchers._utils import assemble_matches, clip_top_n
+from oracle import tfidf as otfidf
+from oracle.assemble import assemble as oracle_assemble
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_pack_utf32_roundtrip():
+    s = ["apple", "", "İstanbul", "a\U0001F600b", "中文 K"]
+    blob, offs = pack_utf32(s)
+    assert offs.tolist() == [0, 5, 5, 13, 16, 20]
+    for i, x in enumerate(s):
+        assert "".join(chr(c) for c in blob[offs[i]:offs[i + 1]]) == x
+    blob, offs = pack_utf32([])
+    assert blob.size == 0 and offs.tolist() == [0]
+    with pytest.raises(TypeError):
+        pack_utf32(["a", 3])
+
+
+@pytest.mark.parametrize("rng", [(1, 1), (1, 3), (3, 3), (3, 6)])
+def test_slot_bounds_cover_every_ngram(rng):
+    strs = ["apple", "", "a", "hello  world!!", "x" * 300, "İK"]
+    _, offs = pack_utf32(strs)
+    slots, occ = ngram_slot_bounds(offs, *rng)
+    for s, b in zip(strs, slots):
+        for clean in (True, False):
+            for rs in (True, False):
+                assert len(otfidf.create_ngrams(s, rng, clean, rs)) <= b
+    assert occ[-1] == slots.sum() and occ[0] == 0
+
+
+def test_assemble_matches_equals_reference_tail_restatement():
+    rng = np.random.default_rng(0)
+    frm = [f"f{i}" for i in range(50)]; to = [f"t{i}" for i in range(20)]
+    idx = rng.integers(-1, 20, (50, 3)).astype(np.int32)
+    val = np.where(idx >= 0, rng.random((50, 3)), 0.0)
+    val[3, 0] = 0.0004
+    got = assemble_matches(frm, to, idx, val)
+    exp = oracle_assemble(frm, to, idx, val)
+    assert list(got.columns) == ["From", "To", "Similarity", "To_2", "Similarity_2", "To_3", "Similarity_3"]
+    for c in got.columns:
+        g = [None if (isinstance(v, float) and np.isnan(v)) else v for v in got[c].tolist()]
+        e = [None if (isinstance(v, float) and np.isnan(v)) else v for v in exp[c].tolist()]
+        assert g == e
+    assert got["To"][3] is None or got["To"].isna()[3]
+    assert clip_top_n(10, ["a", "b", "a"]) == 2 and clip_top_n(10, None) == 10
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    assert lib.pfz_abi_version() == 1
+    header = open(os.path.join(ROOT, "include", "pfz.h")).read()
+    declared = set(re.findall(r"\b(pfz_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.exported_names()), declared ^ set(_lib.exported_names())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pfz_scan_ws_bytes(10) >= 256
+    assert _lib.launch_count() == 0 or _lib.launch_count() > 0
+
+
+def test_plugin_contract():
+    from polyfuzz_b200.matchers import BaseMatcher, TFIDF
+    with pytest.raises(TypeError):
+        BaseMatcher()                                      # tests/models/test_base.py:29-31
+    m = TFIDF(n_gram_range=(2, 3), min_similarity=0.5, top_n=3, model_id="x")
+    assert isinstance(m, BaseMatcher) and m.type == "TF-IDF" and m.model_id == "x"
+    assert m.vectorizer is None and m.tf_idf_to is None
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="CUDA|cuda"):
+        polyfuzz_b200.TFIDF().match(["apple", "apples"], ["apple"])
+
+
+def test_synth_generators_are_seeded():
+    from polyfuzz_b200 import synth
+    a = synth.company_names(200, seed=3); b = synth.company_names(200, seed=3)
+    assert a == b and a != synth.company_names(200, seed=4)
+    u = synth.uniform_strings(100, seed=0)
+    assert all(8 <= len(s) <= 32 for s in u)
+    t = synth.titles(100, seed=1)
+    assert len(t) == 100 and all(len(s) > 0 for s in t)
