@@ -112,11 +112,13 @@ int64_t pfz_scan_ws_bytes(int64_t n);
 
 /* Inverted index of the to-matrix: postings grouped by (term, to-tile of `tile` rows).
  *   seg      int32[n_vocab*(n_tiles)+1]  prefix offsets, entry t*n_tiles+tau = start of (term t, tile tau)
- *   post_idx int32[nnz]  to-row LOCAL to the shard;  post_val float64[nnz]
+ *   post_idx uint16[nnz] to-row LOCAL to its tile (row - tau*tile);  post_val float64[nnz]
+ *   (posting order inside a (term, tile) segment is unspecified -- every to-row occurs at most once
+ *    per term, so the per-pair addition order, ascending term, does not depend on it)
  *   ws: >= pfz_scan_ws_bytes(n_vocab*n_tiles+1) + 4*(n_vocab*n_tiles+1) bytes                         */
 int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double *data, int32_t n_rows,
                     int32_t n_vocab, int32_t tile, int32_t n_tiles,
-                    int32_t *seg, int32_t *post_idx, double *post_val, void *ws, void *stream);
+                    int32_t *seg, uint16_t *post_idx, double *post_val, void *ws, void *stream);
 
 /* top-k of (from CSR) x (to inverted index).
  *   k <= 32.  n_splits > 1 splits the to-tiles over blockIdx.y and writes partial lists
@@ -124,14 +126,19 @@ int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double 
  *   from_index_base + i.  Output indices are GLOBAL: to_index_base + local row.
  *   excl_val/excl_idx (may be NULL): per-row exclusive lower key -- only candidates ranking strictly
  *   AFTER (excl_val[i], excl_idx[i]) are considered (used to page through top_n > 32).
- *   row_counter: int32 on device, zeroed by the callee (dynamic row scheduling).                     */
+ *   row_counter: int32[n_splits] on device, zeroed by the callee (dynamic row scheduling).
+ *   variant: PFZ_K2_LIST  -- touched-list selection, work ~ postings (sparse inputs, e.g. uniform text)
+ *            PFZ_K2_DENSE -- threshold-crossing bitmap + dense accumulator clear (rows that touch a
+ *                            sizeable fraction of every tile, e.g. company names); same results.       */
+#define PFZ_K2_LIST  1
+#define PFZ_K2_DENSE 2
 int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from,
-                   const int32_t *seg, const int32_t *post_idx, const double *post_val,
+                   const int32_t *seg, const uint16_t *post_idx, const double *post_val,
                    int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to,
                    int32_t k, double min_similarity, int32_t self_match,
                    int64_t from_index_base, int64_t to_index_base, int32_t n_splits,
                    const double *excl_val, const int32_t *excl_idx,
-                   int32_t *top_idx, double *top_val, int32_t *row_counter, void *stream);
+                   int32_t *top_idx, double *top_val, int32_t *row_counter, int32_t variant, void *stream);
 
 /* merge n_lists sorted top-k lists per row ([n_lists][n_from][k_in]) into [n_from][k_out];
  * same key.  Used for tile splits and for the per-shard lists after the NCCL all-gather.            */

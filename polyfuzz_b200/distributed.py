@@ -94,7 +94,8 @@ def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, 
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
     idx, val = engine.spcos_topk(csr_from, index, top_n, min_similarity, self_match=self_match,
-                                 from_index_base=from_index_base, to_index_base=to_index_base)
+                                 from_index_base=from_index_base, to_index_base=to_index_base,
+                                 density=vectorizer.density())
     if ev is not None:
         ev[1].record()
         timings.append(ev)

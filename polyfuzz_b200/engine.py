@@ -291,6 +291,14 @@ class NgramTfidf:
                   _p(self._d_vocab), self.n_vocab, _p(self._d_idf), _p(indptr), _p(indices), _p(data), _p(ws), _stream())
         return CsrMatrix(indptr, indices, data, R.n, self.n_vocab)
 
+    def density(self):
+        """Postings visited per scored pair, estimated from the fitted document frequencies:
+        sum_t df_t^2 / n_docs^2 (exact for a self-match).  Chooses the K2 variant."""
+        if self.df is None or not self.n_fit_docs:
+            return None
+        d = self.df.astype(np.float64)
+        return float((d * d).sum() / float(self.n_fit_docs) ** 2)
+
     def fit(self, strings):
         self.fit_rows([strings])
         return self
@@ -299,7 +307,7 @@ class NgramTfidf:
         return self.emit(self.rows(strings))
 
 
-DEFAULT_TILE = int(os.environ.get("PFZ_TILE", "2048"))
+DEFAULT_TILE = int(os.environ.get("PFZ_TILE", "1024"))
 K2_WARPS = 8
 
 
@@ -310,7 +318,7 @@ class SparseIndex:
         n = csr.n_rows
         if tile is None:
             tile = DEFAULT_TILE
-        tile = max(32, min(int(tile), ((max(n, 1) + 31) // 32) * 32))
+        tile = max(64, min(int(tile), ((max(n, 1) + 63) // 64) * 64))
         self.tile = tile
         self.n_to = n
         self.n_vocab = csr.n_cols
@@ -319,7 +327,7 @@ class SparseIndex:
         dev = _dev()
         self.seg = torch.empty(ncell + 1, dtype=torch.int32, device=dev)
         cap = max(csr.indices.numel(), 1)
-        self.post_idx = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.post_idx = torch.empty(cap, dtype=torch.int16, device=dev)          # uint16 tile-local row
         self.post_val = torch.empty(cap, dtype=torch.float64, device=dev)
         ws = _ws((ncell + 1) * 4 + 512 + _lib.load().pfz_scan_ws_bytes(ncell + 1))
         _lib.call("pfz_index_build", _p(csr.indptr), _p(csr.indices), _p(csr.data), n, self.n_vocab, tile,
@@ -333,9 +341,18 @@ def _auto_splits(n_from, n_tiles, sm_count=148):
     return max(1, min(n_tiles, (want + max(n_from, 1) - 1) // max(n_from, 1)))
 
 
+K2_LIST, K2_DENSE = 1, 2
+DENSE_MIN_DENSITY = float(os.environ.get("PFZ_DENSE_MIN_DENSITY", "0.03"))
+K2_VARIANT = {"list": K2_LIST, "dense": K2_DENSE}
+
+
 def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_match=False, from_index_base=0,
-               to_index_base=0, n_splits=None):
-    """K2.  Returns (top_idx int32[n_from,k] GLOBAL to-indices or -1, top_val float64[n_from,k]) on device."""
+               to_index_base=0, n_splits=None, variant="auto", density=None):
+    """K2.  Returns (top_idx int32[n_from,k] GLOBAL to-indices or -1, top_val float64[n_from,k]) on device.
+    variant: "list" | "dense" | "auto" (dense when `density` = postings visited per scored pair is
+    >= DENSE_MIN_DENSITY; both give identical results, they differ in cost model -- see pfz.h)."""
+    if variant == "auto":
+        variant = "dense" if (density is not None and density >= DENSE_MIN_DENSITY) else "list"
     dev = _dev()
     n_from = a.n_rows
     k = int(k)
@@ -355,7 +372,7 @@ def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_mat
         _lib.call("pfz_spcos_topk", _p(a.indptr), _p(a.indices), _p(a.data), n_from, _p(index.seg), _p(index.post_idx),
                   _p(index.post_val), index.n_vocab, index.tile, index.n_tiles, index.n_to, kp, float(min_similarity),
                   int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, _p(excl_v), _p(excl_i),
-                  _p(ti), _p(tv), _p(counter), _stream())
+                  _p(ti), _p(tv), _p(counter), K2_VARIANT[variant], _stream())
         if n_splits > 1:
             oi = torch.empty((max(n_from, 1), kp), dtype=torch.int32, device=dev)
             ov = torch.empty((max(n_from, 1), kp), dtype=torch.float64, device=dev)

@@ -93,11 +93,11 @@ class TFIDF(BaseMatcher):
             self._extract_tf_idf(from_list, None, re_train)
             block = self.vectorizer.transform(from_list[lo:hi])
             idx, val = engine.spcos_topk(block, self._index, top_n, self.min_similarity, self_match=True,
-                                         from_index_base=lo)
+                                         from_index_base=lo, density=self.vectorizer.density())
             return idx, val, top_n
         tf_idf_from, tf_idf_to = self._extract_tf_idf(from_list, to_list, re_train)
         idx, val = engine.spcos_topk(tf_idf_from, self._index, top_n, self.min_similarity,
-                                     self_match=to_list is None)
+                                     self_match=to_list is None, density=self.vectorizer.density())
         return idx, val, top_n
 
     def _extract_tf_idf(self, from_list, to_list=None, re_train=True):

@@ -106,9 +106,10 @@ def test_company_slice_vectoriser_bit_exact(pf, company):
     _csr_eq(v.emit(rows), g["csr_indptr"], g["csr_indices"], g["csr_data"], g["csr_shape"])
 
 
+@pytest.mark.parametrize("variant", ["list", "dense"])
 @pytest.mark.parametrize("tile", [None, 256, 1024])
 @pytest.mark.parametrize("n_splits", [1, 3])
-def test_company_slice_topk_vs_oracle_and_reference(pf, company, tile, n_splits):
+def test_company_slice_topk_vs_oracle_and_reference(pf, company, tile, n_splits, variant):
     polyfuzz_b200, engine = pf
     g, names = company
     k = 10
@@ -116,7 +117,7 @@ def test_company_slice_topk_vs_oracle_and_reference(pf, company, tile, n_splits)
     (rows,) = v.fit_rows([names])
     csr = v.emit(rows)
     index = engine.SparseIndex(csr, tile=tile)
-    idx, val = engine.spcos_topk(csr, index, k, 0.0, self_match=True, n_splits=n_splits)
+    idx, val = engine.spcos_topk(csr, index, k, 0.0, self_match=True, n_splits=n_splits, variant=variant)
     idx, val = idx.cpu().numpy(), val.cpu().numpy()
     a = csr.to_scipy()
     oi, ov = onative.spdot_topn(a, a, k, 0.0, self_match=True)
@@ -152,10 +153,12 @@ def _oracle_two(frm, to, rng=(3, 3), clean=True, rs=True):
     return f, t
 
 
+@pytest.mark.parametrize("variant", ["list", "dense"])
 @pytest.mark.parametrize("k,ms", [(1, 0.0), (5, 0.3), (32, 0.0), (40, 0.0), (70, 0.05)])
-def test_synthetic_two_list_vs_oracle(pf, k, ms):
+def test_synthetic_two_list_vs_oracle(pf, k, ms, variant, monkeypatch):
     polyfuzz_b200, engine = pf
     from polyfuzz_b200 import synth
+    monkeypatch.setattr(engine, "DENSE_MIN_DENSITY", 0.0 if variant == "dense" else 1e9)
     to = synth.company_names(6000, seed=3)
     frm = synth.company_names(2500, seed=4) + ["", "a", "ab", "  ", "!!!", to[17], to[17].lower()]
     m = polyfuzz_b200.TFIDF(min_similarity=ms, top_n=k)

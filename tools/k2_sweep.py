@@ -31,9 +31,15 @@ ip = csr.indptr.cpu().numpy(); nnz = int(ip[-1])
 df = np.bincount(csr.indices[:nnz].cpu().numpy(), minlength=v.n_vocab).astype(np.float64)
 P = float((df * df).sum())
 print(f"n={n} V={v.n_vocab} nnz={nnz} P={P:.4g} fit(stageA+vocab incl. H2D, host idf)={t_fit:.2f} ms emit={t_emit:.2f} ms wall={time.time()-t0:.2f}s")
-for tile in tiles:
+variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["dense", "list"]
+ref = None
+for variant in variants:
+  for tile in tiles:
     idx_obj, t_ix, _ = timed(lambda: engine.SparseIndex(csr, tile=tile), 3, 1)
-    (_, _), t_k2, t_min = timed(lambda: engine.spcos_topk(csr, idx_obj, 10, 0.0, self_match=True, n_splits=1), 5, 2)
+    (oi, ov), t_k2, t_min = timed(lambda: engine.spcos_topk(csr, idx_obj, 10, 0.0, self_match=True, n_splits=1, variant=variant), 5, 2)
+    if ref is None:
+        ref = (oi.clone(), ov.clone())
+    same = bool(torch.equal(oi, ref[0]) and torch.equal(ov, ref[1]))
     pairs = float(n) * n - n
-    print(f"tile={tile:5d} n_tiles={idx_obj.n_tiles:4d} index_build={t_ix:7.2f} ms  K2 median={t_k2:8.2f} ms min={t_min:8.2f} ms  "
+    print(f"{variant:5s} same={same} tile={tile:5d} n_tiles={idx_obj.n_tiles:4d} index_build={t_ix:7.2f} ms  K2 median={t_k2:8.2f} ms min={t_min:8.2f} ms  "
           f"pairs/s={pairs / (t_k2 * 1e-3):.3e}  postings/s={P / (t_k2 * 1e-3):.3e}  B_alg GB/s={(P * 12 + nnz * 12 + n * 120) / (t_k2 * 1e-3) / 1e9:.1f}")
