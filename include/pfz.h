@@ -116,8 +116,9 @@ int64_t pfz_scan_ws_bytes(int64_t n);
  *   (posting order inside a (term, tile) segment is unspecified -- every to-row occurs at most once
  *    per term, so the per-pair addition order, ascending term, does not depend on it)
  *   ws: >= pfz_scan_ws_bytes(n_vocab*n_tiles+1) + 4*(n_vocab*n_tiles+1) bytes                         */
+#define PFZ_INDEX_BANK_ORDER 1   /* arrange each segment so that 16 consecutive postings hit distinct smem banks */
 int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double *data, int32_t n_rows,
-                    int32_t n_vocab, int32_t tile, int32_t n_tiles,
+                    int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t flags,
                     int32_t *seg, uint16_t *post_idx, double *post_val, void *ws, void *stream);
 
 /* top-k of (from CSR) x (to inverted index).

@@ -15,6 +15,7 @@
 //     - no atomics and no block barriers are needed (only __syncwarp between terms).
 //   First touches are detected by acc == 0 (all weights are > 0) and recorded in a per-warp list, so
 //   the selection phase visits touched to-rows only (work ~ postings, not ~ n_from * n_to).
+#include <stdlib.h>
 #include "pfz_common.cuh"
 
 namespace pfz {
@@ -43,6 +44,52 @@ __global__ void index_fill_kernel(const int32_t *__restrict__ indptr, const int3
             const int pos = seg[c] + atomicAdd(&cur[c], 1);
             post_idx[pos] = (uint16_t)(r - tau * tile);
             post_val[pos] = data[p];
+        }
+    }
+}
+
+// Posting order inside a (term, tile) segment is free (see pfz.h), so it is chosen for the consumer:
+// K2's 32 lanes read-modify-write acc[row] as 8-byte words, i.e. two 16-lane transactions over 16
+// double-wide banks.  Each segment is rearranged in "rounds" that contain every (row mod 16) residue at
+// most once, residues ascending, so a 16-lane window rarely holds two rows of the same bank
+// (random order: ~2.8 wavefronts per transaction; rounds: close to 1).
+constexpr int BANK_ORDER_MAX = 512;     // longer segments (only with very large tiles) keep their fill order
+__global__ void __launch_bounds__(128) index_bank_order_kernel(const int32_t *__restrict__ seg, int64_t ncell, uint16_t *__restrict__ post_idx,
+                                                               double *__restrict__ post_val) {
+    __shared__ uint16_t s_idx[4][BANK_ORDER_MAX];
+    __shared__ uint16_t s_rank[4][BANK_ORDER_MAX];
+    __shared__ double s_val[4][BANK_ORDER_MAX];
+    __shared__ int s_cnt[4][16];
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c0 = gw * 32; c0 < ncell; c0 += nw * 32) {
+        // each lane inspects one cell, the warp then serves the cells that need work
+        int s = 0, len = 0;
+        if (c0 + lane < ncell) { s = seg[c0 + lane]; len = seg[c0 + lane + 1] - s; }
+        unsigned todo = __ballot_sync(FULL, len > 16 && len <= BANK_ORDER_MAX);
+        while (todo) {
+            const int src = __ffs(todo) - 1; todo &= todo - 1;
+            const int cs = __shfl_sync(FULL, s, src), cl = __shfl_sync(FULL, len, src);
+            if (lane < 16) s_cnt[w][lane] = 0;
+            __syncwarp();
+            for (int q = lane; q < cl; q += 32) {
+                const uint16_t j = post_idx[cs + q];
+                s_idx[w][q] = j; s_val[w][q] = post_val[cs + q];
+                s_rank[w][q] = (uint16_t)atomicAdd(&s_cnt[w][j & 15], 1);
+            }
+            __syncwarp();
+            int cnt[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) cnt[r] = s_cnt[w][r];
+            for (int q = lane; q < cl; q += 32) {
+                const int r = s_idx[w][q] & 15, i = s_rank[w][q];
+                int pos = 0;
+#pragma unroll
+                for (int r2 = 0; r2 < 16; ++r2) pos += min(cnt[r2], i) + ((r2 < r && cnt[r2] > i) ? 1 : 0);
+                post_idx[cs + pos] = s_idx[w][q];
+                post_val[cs + pos] = s_val[w][q];
+            }
+            __syncwarp();
         }
     }
 }
@@ -177,29 +224,64 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_list_kernel(const SpcosParam
 // Same ownership (one warp = one (from-row, to-tile) unit, private acc[tile]) but tuned for inputs
 // where a from-row touches a sizeable fraction of every tile (company names: ~24 %):
 //   * no touched list: a to-row becomes a candidate the moment its running sum first passes the
-//     current k-th key (partial sums only grow: all weights > 0); candidates are flagged in a tile
-//     bitmap (rare after the first tiles) and examined with their FINAL sum at the end of the unit;
+//     current k-th key (partial sums only grow: all weights > 0); it is flagged in a per-tile byte map
+//     (rare after the first tiles) and examined with its FINAL sum at the end of the unit;
 //   * acc is cleared densely with 16-byte stores (tile/64 instructions per lane);
-//   * per term: one 16-byte broadcast read of {start,len,weight}; up to 4 posting chunks are loaded
-//     before any is consumed (memory-level parallelism without relying on occupancy alone).
-struct __align__(16) TermSeg { int s; int len; double v; };
+//   * the unit's work items (<= 32 consecutive postings of one term) are written to a small table
+//     first, then consumed by a branch-free loop that keeps D items' loads in flight across term
+//     boundaries -- with a large tile only a dozen warps fit per SM, so memory-level parallelism has
+//     to come from inside each warp.
+struct __align__(16) WorkItem { int off; int cnt; double v; };
 
-template <int WARPS>
+// ---- inline-PTX helpers for the dense kernel's inner loop ---------------------------------------
+// Explicit 32-bit shared-window addresses and predicated instructions: the generic-pointer forms made
+// the compiler re-derive the shared window base and wrap every item in convergence barriers.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+// work item {int off; int cnt; double v} with one 16-byte load
+__device__ __forceinline__ void lds_item(unsigned a, unsigned &off, int &cnt, double &v) {
+    unsigned lo, hi;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(off), "=r"(cnt), "=r"(lo), "=r"(hi) : "r"(a) : "memory");
+    v = __hiloint2double((int)hi, (int)lo);
+}
+// lanes below cnt load their posting (tile-local row, weight); the others get the dummy row / weight 0
+__device__ __forceinline__ void ldg_posting(const uint16_t *pi, const double *pv, int lane, int cnt, unsigned dummy, unsigned &jl, double &w) {
+    asm volatile("{ .reg .pred p; setp.lt.s32 p, %2, %3; mov.u32 %0, %4; mov.f64 %1, 0d0000000000000000;\n\t"
+                 "@p ld.global.nc.u16 %0, [%5]; @p ld.global.nc.f64 %1, [%6]; }"
+                 : "=&r"(jl), "=&d"(w) : "r"(lane), "r"(cnt), "r"(dummy), "l"(pi), "l"(pv) : "memory");
+}
+// first time the running sum passes thr: set the row's flag byte, remember that this lane flagged something
+__device__ __forceinline__ void flag_if_crossed(unsigned flag_addr, double old, double nw, double thr, unsigned &any) {
+    asm volatile("{ .reg .pred p, q; .reg .b16 one; mov.b16 one, 1;\n\t"
+                 "setp.gt.f64 p, %1, %3; setp.gt.and.f64 q, %2, %3, !p;\n\t"
+                 "@q st.shared.u8 [%4], one; selp.u32 %0, 1, %0, q; }"
+                 : "+r"(any) : "d"(old), "d"(nw), "d"(thr), "r"(flag_addr) : "memory");
+}
+
+
+template <int WARPS, int D>
 __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosParams P) {
     extern __shared__ __align__(16) unsigned char dyn[];
     const int lane = lane_id();
     const int w = threadIdx.x >> 5;
     const int T = P.tile;
-    const int nwords = T >> 5;
-    // per-warp arena: acc double[T] | terms TermSeg[32] | bitmap uint32[T/32]
-    const size_t arena = (size_t)T * 8 + 32 * sizeof(TermSeg) + (size_t)nwords * 4;
+    const int max_items = (T >> 5) + 32 + 2 * D;
+    // per-warp arena: acc double[T + 2] (row T = dummy for idle lanes) | items WorkItem[max_items] | flags uint8[T + 16]
+    const size_t arena = (size_t)(T + 2) * 8 + (size_t)max_items * sizeof(WorkItem) + (size_t)T + 16;
     unsigned char *base = dyn + (size_t)w * ((arena + 15) & ~(size_t)15);
     double *acc = reinterpret_cast<double *>(base);
-    TermSeg *terms = reinterpret_cast<TermSeg *>(base + (size_t)T * 8);
-    unsigned *bitmap = reinterpret_cast<unsigned *>(base + (size_t)T * 8 + 32 * sizeof(TermSeg));
-    for (int q = lane; q < T; q += 32) acc[q] = 0.0;
-    for (int q = lane; q < nwords; q += 32) bitmap[q] = 0u;
+    WorkItem *items = reinterpret_cast<WorkItem *>(base + (size_t)(T + 2) * 8);
+    unsigned char *flags = base + (size_t)(T + 2) * 8 + (size_t)max_items * sizeof(WorkItem);
+    for (int q = lane; q < T + 2; q += 32) acc[q] = 0.0;
+    for (int q = lane; q < T + 16; q += 32) flags[q] = 0;
     __syncwarp();
+    const unsigned acc_s = smem_u32(acc), items_s = smem_u32(items), flags_s = smem_u32(flags);
+    const uint16_t *pidx_lane = P.post_idx + lane;
+    const double *pval_lane = P.post_val + lane;
+    asm volatile("" : "+l"(pidx_lane), "+l"(pval_lane));          // keep the two base pointers in registers
+    const int32_t *__restrict__ seg = P.seg;
+    const int n_tiles = P.n_tiles, K = P.k;
 
     const int split = blockIdx.y;
     const int tiles_per = (P.n_tiles + P.n_splits - 1) / P.n_splits;
@@ -218,6 +300,10 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
         const int m = P.a_indptr[i + 1] - a0;
         double tv = P.min_sim; int ti = -1;
         double kv = P.min_sim; int ki = -1;
+        // pass(x) := x > thr encodes "the running sum ranks before the k-th key": thr = kv while the list is
+        // not full (strict; untouched sums are 0) and the double just below kv once it is (inclusive: ties are
+        // settled on the index at the end of the unit)
+        double thr = fmax(P.min_sim, 0.0);
         double xv = 0.0; int xi = -1; bool has_x = false;
         if (P.excl_val) { xv = P.excl_val[i]; xi = P.excl_idx[i]; has_x = xi >= 0; }
         const int64_t self_j = P.from_base + i - P.to_base;
@@ -232,90 +318,108 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
 
         for (int it = 0; it < ntau; ++it) {
             int tau = first_tau + it; if (tau >= tau_hi) tau -= ntau;
-            bool any_post = false;
+            bool any_post = false; unsigned crossed_any = 0u;
             for (int tb = 0; tb < m; tb += 32) {
                 const int kk = tb + lane;
                 int s = 0, len = 0; double v = 0.0;
                 if (kk < m) {
                     int t;
                     if (m <= 32) { t = t_reg; v = v_reg; } else { t = P.a_indices[a0 + kk]; v = P.a_data[a0 + kk]; }
-                    const int64_t c = (int64_t)t * P.n_tiles + tau;
-                    const int e = P.seg[c + 1];
-                    s = (m <= 32 && it > 0 && tau != tau_lo) ? prev_end : P.seg[c];
+                    const int64_t c = (int64_t)t * n_tiles + tau;
+                    const int e = seg[c + 1];
+                    s = (m <= 32 && it > 0 && tau != tau_lo) ? prev_end : seg[c];
                     prev_end = e;
                     len = e - s;
                 }
-                TermSeg me; me.s = s; me.len = len; me.v = v;
-                terms[lane] = me;
-                unsigned live = __ballot_sync(FULL, len > 0);
-                __syncwarp();
-                any_post |= live != 0u;
-                while (live) {                                   // ascending lane == ascending term
-                    const int src = __ffs(live) - 1; live &= live - 1;
-                    const TermSeg ts = terms[src];               // 16-byte broadcast
-                    const uint16_t *pi = P.post_idx + ts.s;
-                    const double *pv = P.post_val + ts.s;
-                    for (int c0 = 0; c0 < ts.len; c0 += 128) {
-                        int jl[4]; double wv[4];
+                // work-item table: lane k appends its ceil(len/32) items at the exclusive prefix of the counts.
+                // A to-row may occur under several terms, so a term group can need more items than the table
+                // holds (cap >= one term's worth): it is then consumed in batches of whole terms, in order.
+                const int nch = (len + 31) >> 5;
+                const int incl = warp_incl_scan(nch);
+                const int n_total = __shfl_sync(FULL, incl, 31);
+                if (n_total == 0) continue;
+                any_post = true;
+                const int cap = (T >> 5) + 32;
+                for (int start = 0; start < n_total;) {
+                    const bool inb = nch > 0 && incl - nch >= start && incl <= start + cap;
+                    const unsigned bm = __ballot_sync(FULL, inb);
+                    const int endv = __shfl_sync(FULL, incl, 31 - __clz(bm));
+                    const int N = endv - start;
+                    if (inb) {
+                        int o = incl - nch - start, so = s, rem = len;
+                        while (rem > 0) { WorkItem wi; wi.off = so; wi.cnt = rem; wi.v = v; items[o] = wi; ++o; so += 32; rem -= 32; }
+                    }
+                    if (lane < 2 * D) { WorkItem wi; wi.off = 0; wi.cnt = 0; wi.v = 0.0; items[N + lane] = wi; }   // padding
+                    __syncwarp();
+                    // branch-free consumer: slot d holds item b+d; after it is consumed the slot is refilled with
+                    // item b+d+D (padding items have cnt = 0, so no guard is needed).  Idle lanes add 0 to the dummy
+                    // row T.  No warp barrier between items: the loop body has no branch, the warp stays converged
+                    // and its shared-memory instructions complete in program order.
+                    unsigned rj[D]; double rw[D], rv[D];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int q = c0 + u * 32 + lane;
-                            jl[u] = -1; wv[u] = 0.0;
-                            if (q < ts.len) { jl[u] = pi[q]; wv[u] = pv[q]; }
-                        }
-                        bool cross = false; int cj = 0;
+                    for (int d = 0; d < D; ++d) {
+                        unsigned off; int cnt;
+                        lds_item(items_s + d * 16, off, cnt, rv[d]);
+                        ldg_posting(pidx_lane + off, pval_lane + off, lane, cnt, (unsigned)T, rj[d], rw[d]);
+                    }
+                    unsigned it_s = items_s + D * 16;
+                    for (int b = 0; b < N; b += D) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (jl[u] >= 0) {
-                                const double old = acc[jl[u]];
-                                const double nw = __dadd_rn(old, __dmul_rn(ts.v, wv[u]));
-                                acc[jl[u]] = nw;
-                                // first time the running sum passes the k-th key (ties: inclusive once the list is full)
-                                const bool pn = (nw > kv) || (nw == kv && ki >= 0);
-                                const bool po = (old > kv) || (old == kv && ki >= 0);
-                                if (pn && !po) { atomicOr(&bitmap[jl[u] >> 5], 1u << (jl[u] & 31)); }
-                            }
+                        for (int d = 0; d < D; ++d) {
+                            const unsigned a = acc_s + rj[d] * 8u;
+                            const double old = lds_f64(a);
+                            const double nw = __dadd_rn(old, __dmul_rn(rv[d], rw[d]));
+                            sts_f64(a, nw);
+                            flag_if_crossed(flags_s + rj[d], old, nw, thr, crossed_any);
+                            unsigned off; int cnt;
+                            lds_item(it_s + d * 16, off, cnt, rv[d]);
+                            ldg_posting(pidx_lane + off, pval_lane + off, lane, cnt, (unsigned)T, rj[d], rw[d]);
                         }
-                        (void)cross; (void)cj;
+                        it_s += D * 16;
                     }
                     __syncwarp();
+                    start = endv;
                 }
             }
             if (!any_post) continue;
-            // candidates: bitmap words -> final sums -> exact key test -> insertion
-            for (int w0 = 0; w0 < nwords; w0 += 32) {
-                unsigned bits = 0u;
-                if (w0 + lane < nwords) { bits = bitmap[w0 + lane]; if (bits) bitmap[w0 + lane] = 0u; }
-                while (__ballot_sync(FULL, bits != 0u)) {
-                    double sc = 0.0; int j = -1; bool cand = false;
-                    if (bits) {
-                        const int b = __ffs(bits) - 1; bits &= bits - 1;
-                        const int jl = ((w0 + lane) << 5) + b;
-                        sc = acc[jl];
-                        const int jloc = tau * T + jl;
-                        j = (int)(P.to_base + jloc);
-                        cand = key_before(sc, j, kv, ki);
-                        if (P.self_match && (int64_t)jloc == self_j) cand = false;
-                        if (has_x && !key_before(xv, xi, sc, j)) cand = false;
-                    }
-                    unsigned cm = __ballot_sync(FULL, cand);
-                    while (cm) {
-                        const int src = __ffs(cm) - 1;
-                        const double cs = shfl_d(sc, src);
-                        const int cjx = __shfl_sync(FULL, j, src);
-                        const bool stays = (lane < P.k) && key_before(tv, ti, cs, cjx);
-                        const int pos = __popc(__ballot_sync(FULL, stays));
-                        const double uv = __shfl_up_sync(FULL, tv, 1);
-                        const int ui = __shfl_up_sync(FULL, ti, 1);
-                        if (lane > pos) { tv = uv; ti = ui; }
-                        else if (lane == pos) { tv = cs; ti = cjx; }
-                        kv = shfl_d(tv, P.k - 1);
-                        ki = __shfl_sync(FULL, ti, P.k - 1);
-                        // prune: drop the inserted lane and everything the new k-th key now rejects
-                        cand = cand && lane != src && key_before(sc, j, kv, ki);
-                        cm = __ballot_sync(FULL, cand);
+            // candidates: flagged to-rows -> final sums -> exact key test -> insertion
+            if (__any_sync(FULL, crossed_any != 0u)) {
+                for (int w0 = 0; w0 < T; w0 += 128) {               // 4 flag bytes per lane per step
+                    unsigned bits = 0u;
+                    const int q4 = w0 + lane * 4;
+                    if (q4 < T) { bits = *reinterpret_cast<const unsigned *>(flags + q4); if (bits) *reinterpret_cast<unsigned *>(flags + q4) = 0u; }
+                    while (__ballot_sync(FULL, bits != 0u)) {
+                        double sc = 0.0; int j = -1; bool cand = false;
+                        if (bits) {
+                            const int b8 = (__ffs(bits) - 1) >> 3; bits &= ~(0xffu << (b8 * 8));
+                            const int jl = q4 + b8;
+                            sc = acc[jl];
+                            const int jloc = tau * T + jl;
+                            j = (int)(P.to_base + jloc);
+                            cand = key_before(sc, j, kv, ki);
+                            if (P.self_match && (int64_t)jloc == self_j) cand = false;
+                            if (has_x && !key_before(xv, xi, sc, j)) cand = false;
+                        }
+                        unsigned cm = __ballot_sync(FULL, cand);
+                        while (cm) {
+                            const int src = __ffs(cm) - 1;
+                            const double cs = shfl_d(sc, src);
+                            const int cjx = __shfl_sync(FULL, j, src);
+                            const bool stays = (lane < K) && key_before(tv, ti, cs, cjx);
+                            const int pos = __popc(__ballot_sync(FULL, stays));
+                            const double uv = __shfl_up_sync(FULL, tv, 1);
+                            const int ui = __shfl_up_sync(FULL, ti, 1);
+                            if (lane > pos) { tv = uv; ti = ui; }
+                            else if (lane == pos) { tv = cs; ti = cjx; }
+                            kv = shfl_d(tv, K - 1);
+                            ki = __shfl_sync(FULL, ti, K - 1);
+                            // prune: drop the inserted lane and everything the new k-th key now rejects
+                            cand = cand && lane != src && key_before(sc, j, kv, ki);
+                            cm = __ballot_sync(FULL, cand);
+                        }
                     }
                 }
+                thr = (ki >= 0) ? __longlong_as_double(__double_as_longlong(kv) - 1) : fmax(kv, 0.0);
             }
             __syncwarp();
             // dense clear, 16 B per lane per store
@@ -326,8 +430,8 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
             }
             __syncwarp();
         }
-        if (lane < P.k) {
-            const size_t o = ((size_t)split * P.n_from + i) * P.k + lane;
+        if (lane < K) {
+            const size_t o = ((size_t)split * P.n_from + i) * K + lane;
             P.top_idx[o] = ti;
             P.top_val[o] = (ti >= 0) ? tv : 0.0;
         }
@@ -390,7 +494,7 @@ using namespace pfz;
 extern "C" {
 
 int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double *data, int32_t n_rows, int32_t n_vocab, int32_t tile,
-                    int32_t n_tiles, int32_t *seg, uint16_t *post_idx, double *post_val, void *ws, void *stream) {
+                    int32_t n_tiles, int32_t flags, int32_t *seg, uint16_t *post_idx, double *post_val, void *ws, void *stream) {
     PFZ_REQUIRE(tile > 0 && tile <= 65536, "pfz_index_build: tile %d out of range (1..65536)", tile);
     PFZ_REQUIRE((int64_t)n_tiles * tile >= n_rows, "pfz_index_build: n_tiles*tile < n_rows");
     const int64_t ncell = (int64_t)n_vocab * n_tiles;
@@ -410,6 +514,10 @@ int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double 
         index_fill_kernel<<<grid_for2((int64_t)n_rows * 32, 256, 148 * 16), 256, 0, st>>>(indptr, indices, data, n_rows, tile, n_tiles, seg, cur,
                                                                                             post_idx, post_val);
         PFZ_LAUNCH_OK();
+        if (flags & PFZ_INDEX_BANK_ORDER) {
+            index_bank_order_kernel<<<grid_for2(ncell, 128, 148 * 16), 128, 0, st>>>(seg, ncell, post_idx, post_val);
+            PFZ_LAUNCH_OK();
+        }
     }
     return 0;
 }
@@ -450,9 +558,13 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
         constexpr int WARPS = 8;
         return launch(spcos_list_kernel<WARPS>, WARPS, (size_t)WARPS * tile * 10);
     }
-    constexpr int WARPS = 4;
-    const size_t arena = (((size_t)tile * 8 + 32 * sizeof(TermSeg) + (size_t)(tile >> 5) * 4) + 15) & ~(size_t)15;
-    return launch(spcos_dense_kernel<WARPS>, WARPS, (size_t)WARPS * arena);
+    constexpr int WARPS = 2;
+    auto arena_of = [&](int D) { return (((size_t)(tile + 2) * 8 + (size_t)((tile >> 5) + 32 + 2 * D) * sizeof(WorkItem) + (size_t)tile + 16) + 15) & ~(size_t)15; };
+    const char *env_d = getenv("PFZ_K2_DEPTH");                  // developer knob (pipeline depth); default 4
+    const int depth = env_d ? atoi(env_d) : 4;
+    if (depth == 8) return launch(spcos_dense_kernel<WARPS, 8>, WARPS, (size_t)WARPS * arena_of(8));
+    if (depth == 2) return launch(spcos_dense_kernel<WARPS, 2>, WARPS, (size_t)WARPS * arena_of(2));
+    return launch(spcos_dense_kernel<WARPS, 4>, WARPS, (size_t)WARPS * arena_of(4));
 }
 
 int pfz_topk_merge(const int32_t *idx, const double *val, int32_t n_lists, int32_t n_from, int32_t k_in, int32_t k_out, int32_t *out_idx,

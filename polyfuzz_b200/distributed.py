@@ -84,7 +84,7 @@ def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, 
         else:
             rows_to, rows_from = vectorizer.fit_staged(staged, counted=counted, comm=comm)
         csr_to = vectorizer.emit(rows_to)
-        index = engine.SparseIndex(csr_to, tile=tile)
+        index = engine.SparseIndex(csr_to, tile=tile, variant=engine.choose_variant(vectorizer.density()))
         csr_from = csr_to if same else vectorizer.emit(rows_from)
     else:
         csr_to = None
@@ -94,8 +94,7 @@ def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, 
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
     idx, val = engine.spcos_topk(csr_from, index, top_n, min_similarity, self_match=self_match,
-                                 from_index_base=from_index_base, to_index_base=to_index_base,
-                                 density=vectorizer.density())
+                                 from_index_base=from_index_base, to_index_base=to_index_base)
     if ev is not None:
         ev[1].record()
         timings.append(ev)

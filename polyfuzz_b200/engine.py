@@ -307,17 +307,20 @@ class NgramTfidf:
         return self.emit(self.rows(strings))
 
 
-DEFAULT_TILE = int(os.environ.get("PFZ_TILE", "1024"))
+# to-tile rows per K2 variant: the list kernel wants many small per-warp arenas (occupancy), the dense
+# kernel few large ones (long segments; it pipelines its own loads)
+DEFAULT_TILE = {"list": int(os.environ.get("PFZ_TILE_LIST", "512")), "dense": int(os.environ.get("PFZ_TILE_DENSE", "1024"))}
 K2_WARPS = 8
 
 
 class SparseIndex:
     """Inverted index of a to-matrix shard: postings grouped by (term, to-tile)."""
 
-    def __init__(self, csr: CsrMatrix, tile=None):
+    def __init__(self, csr: CsrMatrix, tile=None, variant="list"):
         n = csr.n_rows
+        self.variant = variant
         if tile is None:
-            tile = DEFAULT_TILE
+            tile = DEFAULT_TILE[variant]
         tile = max(64, min(int(tile), ((max(n, 1) + 63) // 64) * 64))
         self.tile = tile
         self.n_to = n
@@ -330,8 +333,15 @@ class SparseIndex:
         self.post_idx = torch.empty(cap, dtype=torch.int16, device=dev)          # uint16 tile-local row
         self.post_val = torch.empty(cap, dtype=torch.float64, device=dev)
         ws = _ws((ncell + 1) * 4 + 512 + _lib.load().pfz_scan_ws_bytes(ncell + 1))
+        flags = 1 if os.environ.get("PFZ_BANK_ORDER", "1") != "0" else 0
         _lib.call("pfz_index_build", _p(csr.indptr), _p(csr.indices), _p(csr.data), n, self.n_vocab, tile,
-                  self.n_tiles, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(ws), _stream())
+                  self.n_tiles, flags, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(ws), _stream())
+
+
+def choose_variant(density):
+    """dense when `density` = postings visited per scored pair (NgramTfidf.density()) is at least
+    DENSE_MIN_DENSITY, else list."""
+    return "dense" if (density is not None and density >= DENSE_MIN_DENSITY) else "list"
 
 
 def _auto_splits(n_from, n_tiles, sm_count=148):
@@ -347,12 +357,12 @@ K2_VARIANT = {"list": K2_LIST, "dense": K2_DENSE}
 
 
 def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_match=False, from_index_base=0,
-               to_index_base=0, n_splits=None, variant="auto", density=None):
+               to_index_base=0, n_splits=None, variant="auto"):
     """K2.  Returns (top_idx int32[n_from,k] GLOBAL to-indices or -1, top_val float64[n_from,k]) on device.
-    variant: "list" | "dense" | "auto" (dense when `density` = postings visited per scored pair is
-    >= DENSE_MIN_DENSITY; both give identical results, they differ in cost model -- see pfz.h)."""
+    variant: "list" | "dense" | "auto" (= the variant the index was tiled for, see choose_variant);
+    both give identical results, they differ in cost model -- see pfz.h."""
     if variant == "auto":
-        variant = "dense" if (density is not None and density >= DENSE_MIN_DENSITY) else "list"
+        variant = index.variant
     dev = _dev()
     n_from = a.n_rows
     k = int(k)

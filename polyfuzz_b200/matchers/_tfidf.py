@@ -93,11 +93,11 @@ class TFIDF(BaseMatcher):
             self._extract_tf_idf(from_list, None, re_train)
             block = self.vectorizer.transform(from_list[lo:hi])
             idx, val = engine.spcos_topk(block, self._index, top_n, self.min_similarity, self_match=True,
-                                         from_index_base=lo, density=self.vectorizer.density())
+                                         from_index_base=lo)
             return idx, val, top_n
         tf_idf_from, tf_idf_to = self._extract_tf_idf(from_list, to_list, re_train)
         idx, val = engine.spcos_topk(tf_idf_from, self._index, top_n, self.min_similarity,
-                                     self_match=to_list is None, density=self.vectorizer.density())
+                                     self_match=to_list is None)
         return idx, val, top_n
 
     def _extract_tf_idf(self, from_list, to_list=None, re_train=True):
@@ -123,7 +123,7 @@ class TFIDF(BaseMatcher):
                 self._index = None
             tf_idf_from = self._device_to()
         if self._index is None:
-            self._index = engine.SparseIndex(self._device_to())
+            self._index = engine.SparseIndex(self._device_to(), variant=engine.choose_variant(vec.density()))
         return tf_idf_from, self.tf_idf_to
 
     def _match_sharded(self, comm, from_list, to_list, re_train, top_n, from_block=None):

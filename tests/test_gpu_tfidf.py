@@ -116,8 +116,8 @@ def test_company_slice_topk_vs_oracle_and_reference(pf, company, tile, n_splits,
     v = engine.NgramTfidf((3, 3), True, True)
     (rows,) = v.fit_rows([names])
     csr = v.emit(rows)
-    index = engine.SparseIndex(csr, tile=tile)
-    idx, val = engine.spcos_topk(csr, index, k, 0.0, self_match=True, n_splits=n_splits, variant=variant)
+    index = engine.SparseIndex(csr, tile=tile, variant=variant)
+    idx, val = engine.spcos_topk(csr, index, k, 0.0, self_match=True, n_splits=n_splits)
     idx, val = idx.cpu().numpy(), val.cpu().numpy()
     a = csr.to_scipy()
     oi, ov = onative.spdot_topn(a, a, k, 0.0, self_match=True)
@@ -234,3 +234,19 @@ def test_from_block_is_a_row_block_of_the_self_match(pf):
     full = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=4).match(names)
     blk = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=4).match(names, from_block=(1000, 1800))
     assert blk.reset_index(drop=True).equals(full.iloc[1000:1800].reset_index(drop=True))
+
+
+@pytest.mark.parametrize("variant", ["list", "dense"])
+def test_every_row_shares_many_heavy_terms(pf, variant, monkeypatch):
+    """All rows share ~20 trigrams, so every (term, tile) segment is the full tile: per-unit work far
+    exceeds the dense kernel's work-item table (batched consumption) and every accumulator gets ~20
+    additions in term order."""
+    polyfuzz_b200, engine = pf
+    monkeypatch.setattr(engine, "DENSE_MIN_DENSITY", 0.0 if variant == "dense" else 1e9)
+    names = [f"alpha beta gamma delta {i:05d} {'x' * (i % 7)}{i % 13}" for i in range(2600)]
+    m = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=7)
+    idx, val, k = m.match_arrays(names)
+    a = m.tf_idf_to.to_scipy()
+    oi, ov = onative.spdot_topn(a, a, k, 0.0, self_match=True, n_threads=8)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(val.cpu().numpy(), ov)

@@ -1,0 +1,13 @@
+import sys, os
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import torch
+from polyfuzz_b200 import engine, synth
+n = int(sys.argv[1]); tile = int(sys.argv[2]); variant = sys.argv[3]
+names = synth.company_names(n, seed=0)
+v = engine.NgramTfidf((3, 3), True, True)
+(rows,) = v.fit_rows([names]); csr = v.emit(rows)
+torch.cuda.synchronize(); print("vectorised", flush=True)
+ix = engine.SparseIndex(csr, tile=tile, variant=variant)
+torch.cuda.synchronize(); print("index", flush=True)
+oi, ov = engine.spcos_topk(csr, ix, 10, 0.0, self_match=True, n_splits=1)
+torch.cuda.synchronize(); print("k2 done", oi[:2].tolist(), flush=True)

@@ -35,7 +35,7 @@ variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["dense", "list"]
 ref = None
 for variant in variants:
   for tile in tiles:
-    idx_obj, t_ix, _ = timed(lambda: engine.SparseIndex(csr, tile=tile), 3, 1)
+    idx_obj, t_ix, _ = timed(lambda: engine.SparseIndex(csr, tile=tile, variant=variant), 3, 1)
     (oi, ov), t_k2, t_min = timed(lambda: engine.spcos_topk(csr, idx_obj, 10, 0.0, self_match=True, n_splits=1, variant=variant), 5, 2)
     if ref is None:
         ref = (oi.clone(), ov.clone())

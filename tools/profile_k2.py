@@ -7,7 +7,7 @@ n = int(sys.argv[1]); tile = int(sys.argv[2]); variant = sys.argv[3]; reps = int
 names = synth.company_names(n, seed=0)
 v = engine.NgramTfidf((3, 3), True, True)
 (rows,) = v.fit_rows([names]); csr = v.emit(rows)
-ix = engine.SparseIndex(csr, tile=tile)
+ix = engine.SparseIndex(csr, tile=tile, variant=variant)
 for _ in range(reps):
     engine.spcos_topk(csr, ix, 10, 0.0, self_match=True, n_splits=1, variant=variant)
 torch.cuda.synchronize()
