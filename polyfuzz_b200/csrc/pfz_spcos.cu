@@ -251,7 +251,22 @@ __device__ __forceinline__ void ldg_posting(const uint16_t *pi, const double *pv
                  "@p ld.global.nc.u16 %0, [%5]; @p ld.global.nc.f64 %1, [%6]; }"
                  : "=&r"(jl), "=&d"(w) : "r"(lane), "r"(cnt), "r"(dummy), "l"(pi), "l"(pv) : "memory");
 }
-// first time the running sum passes thr: set the row's flag byte, remember that this lane flagged something
+// The whole read-modify-write of one posting.  Idle lanes (row == dummy) issue no shared-memory access at
+// all (a shared dummy row would cost an extra bank wavefront per half-warp).  The product is rounded
+// before the add (mul.rn + add.rn are never contracted), as in the reference's scalar loop.  When the
+// running sum passes thr for the first time the row's flag byte is set and `any` records it.
+__device__ __forceinline__ void rmw_posting(unsigned acc_s, unsigned flags_s, unsigned row, unsigned dummy, double v, double w, double thr,
+                                            unsigned &any) {
+    asm volatile("{ .reg .pred p, q, r; .reg .f64 o, n, pr; .reg .b16 one; .reg .u32 a, f;\n\t"
+                 "setp.ne.u32 p, %3, %4; mov.f64 o, 0d0000000000000000;\n\t"
+                 "shl.b32 a, %3, 3; add.u32 a, a, %1; add.u32 f, %2, %3;\n\t"
+                 "@p ld.shared.f64 o, [a];\n\t"
+                 "mul.rn.f64 pr, %5, %6; add.rn.f64 n, o, pr;\n\t"
+                 "@p st.shared.f64 [a], n;\n\t"
+                 "setp.gt.f64 q, o, %7; setp.gt.and.f64 r, n, %7, !q; mov.b16 one, 1;\n\t"
+                 "@r st.shared.u8 [f], one; selp.u32 %0, 1, %0, r; }"
+                 : "+r"(any) : "r"(acc_s), "r"(flags_s), "r"(row), "r"(dummy), "d"(v), "d"(w), "d"(thr) : "memory");
+}
 __device__ __forceinline__ void flag_if_crossed(unsigned flag_addr, double old, double nw, double thr, unsigned &any) {
     asm volatile("{ .reg .pred p, q; .reg .b16 one; mov.b16 one, 1;\n\t"
                  "setp.gt.f64 p, %1, %3; setp.gt.and.f64 q, %2, %3, !p;\n\t"
@@ -366,11 +381,7 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                     for (int b = 0; b < N; b += D) {
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
-                            const unsigned a = acc_s + rj[d] * 8u;
-                            const double old = lds_f64(a);
-                            const double nw = __dadd_rn(old, __dmul_rn(rv[d], rw[d]));
-                            sts_f64(a, nw);
-                            flag_if_crossed(flags_s + rj[d], old, nw, thr, crossed_any);
+                            rmw_posting(acc_s, flags_s, rj[d], (unsigned)T, rv[d], rw[d], thr, crossed_any);
                             unsigned off; int cnt;
                             lds_item(it_s + d * 16, off, cnt, rv[d]);
                             ldg_posting(pidx_lane + off, pval_lane + off, lane, cnt, (unsigned)T, rj[d], rw[d]);

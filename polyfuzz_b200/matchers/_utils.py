@@ -1,9 +1,28 @@
 """Result assembly shared by the matchers -- the tail of polyfuzz/models/_utils.py:104-125, built
-column-wise from the top-k arrays instead of through a (1+2k) x n unicode ndarray."""
+column-wise from the top-k arrays instead of through a (1+2k) x n unicode ndarray.
+
+The string columns are gathered with Arrow (`take` on one Arrow array of the to_list, one thread per
+column, GIL released) and handed to pandas as its native `str` columns -- the dtype the reference's
+frame has under pandas 3 -- without per-element Python work or dtype inference."""
+from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional
 
 import numpy as np
 import pandas as pd
+
+try:
+    import pyarrow as pa
+except Exception:                                        # pragma: no cover
+    pa = None
+
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=8, thread_name_prefix="pfz-assemble")
+    return _POOL
 
 
 def clip_top_n(top_n: int, to_list: Optional[List[str]]) -> int:
@@ -13,23 +32,53 @@ def clip_top_n(top_n: int, to_list: Optional[List[str]]) -> int:
     return top_n
 
 
+def _str_dtype():
+    try:
+        dt = pd.StringDtype(na_value=np.nan)
+        if pa is not None and dt.storage == "pyarrow":
+            return dt
+    except Exception:
+        pass
+    return None
+
+
 def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarray) -> pd.DataFrame:
     """top_idx int32[n,k] (global to-index, -1 = none), top_val float64[n,k] (unrounded scores).
     Columns From, To, Similarity, To_2, Similarity_2, ... ; similarities rounded to 3 decimals
     (_utils.py:102); Similarity < 0.001 -> 0.0 and To -> None (_utils.py:119-123)."""
+    same = to_list is None or to_list is from_list
     if to_list is None:
         to_list = from_list
     n, k = top_idx.shape
+    sims_all = np.round(top_val, 3)
+    low_all = (sims_all < 0.001) | (top_idx < 0)
+    sims_all = np.where(low_all, 0.0, sims_all)
+    names = ["To" if r == 0 else f"To_{r + 1}" for r in range(k)]
+    snames = ["Similarity" if r == 0 else f"Similarity_{r + 1}" for r in range(k)]
+    dt = _str_dtype()
+    cols = {}
+    if dt is not None and n > 0:
+        AT = dt.construct_array_type()
+        to_pa = pa.array(to_list, type=pa.large_string())
+        from_pa = to_pa if same else pa.array(from_list, type=pa.large_string())
+        cols["From"] = pd.Series(AT(from_pa, dtype=dt), copy=False)
+
+        def gather(r):
+            ia = pa.array(np.where(low_all[:, r], 0, top_idx[:, r]), mask=np.ascontiguousarray(low_all[:, r]))
+            return to_pa.take(ia)
+
+        taken = list(_pool().map(gather, range(k))) if (k > 1 and n >= 20000) else [gather(r) for r in range(k)]
+        for r in range(k):
+            cols[names[r]] = pd.Series(AT(taken[r], dtype=dt), copy=False)
+            cols[snames[r]] = sims_all[:, r]
+        return pd.DataFrame(cols, copy=False)
+    # generic path (no Arrow-backed str dtype): object columns, explicit dtype so pandas infers nothing
     to_arr = np.empty(len(to_list) + 1, dtype=object)
     to_arr[:-1] = to_list
     to_arr[-1] = None
-    cols = {"From": list(from_list)}
+    cols["From"] = pd.Series(list(from_list), dtype=object)
     for r in range(k):
-        sims = np.round(top_val[:, r], 3)
-        idx = top_idx[:, r].astype(np.int64)
-        low = (sims < 0.001) | (idx < 0)
-        sims = np.where(low, 0.0, sims)
-        idx = np.where(low, len(to_list), idx)
-        cols["To" if r == 0 else f"To_{r + 1}"] = to_arr[idx]
-        cols["Similarity" if r == 0 else f"Similarity_{r + 1}"] = sims
+        idx = np.where(low_all[:, r], len(to_list), top_idx[:, r].astype(np.int64))
+        cols[names[r]] = pd.Series(to_arr[idx], dtype=object)
+        cols[snames[r]] = sims_all[:, r]
     return pd.DataFrame(cols)
