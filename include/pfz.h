@@ -147,6 +147,36 @@ int pfz_topk_merge(const int32_t *idx, const double *val, int32_t n_lists, int32
                    int32_t k_out, int32_t *out_idx, double *out_val, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K3  all-pairs edit distance with a fused per-row arg-best.
+ * Replaces: rapidfuzz process.extractOne / scorer loops as called at polyfuzz/models/_rapidfuzz.py:99-113
+ *           and polyfuzz/models/_distance.py:89-102 (np.argmax = first maximum).
+ * Symbols are bytes: sym_table (uint8[0x110000]) maps the code points of the from-strings to 1..255
+ * and everything else to 0 (the host batches from-strings whose joint alphabet exceeds 255).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* to-list layout: `order` = to-rows sorted by length (ascending); sorted position p lives in group p/32,
+ * lane p%32; group g occupies ceil(maxlen_g/4) x 32 uint32 words starting at grp_word_off[g]
+ * (4 symbols per word, lane-interleaved).  slen[p] receives the length of sorted string p.          */
+int pfz_lev_pack(const uint32_t *to_blob, const int64_t *to_offsets, const int32_t *order, int32_t n_to,
+                 const uint8_t *sym_table, const int64_t *grp_word_off, uint32_t *packed, int32_t *slen, void *stream);
+
+/* scores the from-strings listed in from_ids (all of one word class: n_words = 0 -> length <= 32 (one
+ * 32-bit word), 1/2/4/8/16 -> length <= 64*n_words) against every to-string.
+ *   metric: PFZ_METRIC_*; for NORM_LEV / RATIO a candidate needs score >= score_cutoff
+ *   exclude_self: skip to-row == from-row + self_shift
+ *   part_*: [n_splits][n_from] partial bests (merge with pfz_lev_merge); ties -> lowest to-index
+ *   matrix (may be NULL): int32 [n_from][matrix_ld] full distance matrix (Levenshtein or Indel)
+ *   counter: int32[n_splits], zeroed by the callee                                                   */
+int pfz_lev_argbest(const uint32_t *from_blob, const int64_t *from_offsets, int32_t n_from, const int32_t *from_ids,
+                    int32_t n_ids, int32_t n_words, const uint8_t *sym_table, const uint32_t *packed,
+                    const int64_t *grp_word_off, const int32_t *slen, const int32_t *sorig, int32_t n_to,
+                    int32_t metric, double score_cutoff, int32_t exclude_self, int64_t self_shift, int32_t n_splits,
+                    int32_t *part_idx, double *part_score, int32_t *part_dist, int32_t *matrix, int64_t matrix_ld,
+                    int32_t *counter, void *stream);
+int pfz_lev_merge(const int32_t *part_idx, const double *part_score, const int32_t *part_dist, int32_t n_splits,
+                  int32_t n_from, int32_t *best_idx, double *best_score, int32_t *best_dist, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * End-to-end convenience entry with HOST buffers (what a foreign-language binding would call):
  * self- or two-list TF-IDF match, H2D + K1 + K2 + D2H inside.  See INTEGRATION.md.
  * ---------------------------------------------------------------------------------------------- */

@@ -1,4 +1,5 @@
 from ._base import BaseMatcher
 from ._tfidf import TFIDF
+from ._rapidfuzz import RapidFuzz, EditDistance
 
-__all__ = ["BaseMatcher", "TFIDF"]
+__all__ = ["BaseMatcher", "TFIDF", "RapidFuzz", "EditDistance"]

@@ -1,0 +1,95 @@
+"""RapidFuzz / EditDistance matchers -- drop-ins for polyfuzz.models.RapidFuzz
+(polyfuzz/models/_rapidfuzz.py:11-113) and polyfuzz.models.EditDistance
+(polyfuzz/models/_distance.py:12-102) whose all-pairs scoring runs on the GPU (K3).
+
+Scorers: the GPU kernel implements rapidfuzz's `fuzz.ratio` (normalised Indel, the default of the
+reference's EditDistance) and the normalised Levenshtein similarity.  A scorer may be given as
+  * a name: "ratio" | "levenshtein" (alias "norm_lev"), or
+  * a rapidfuzz callable whose __name__ is `ratio` or `normalized_similarity` (when rapidfuzz is installed).
+Other rapidfuzz scorers (WRatio, partial_*, token_*) and arbitrary Python callables cannot be compiled
+to the device and raise NotImplementedError -- there is no CPU fallback.
+Deviations from the reference, both documented reference bugs: a self-match excludes
+index i only (the reference mutates the shared to_list, _rapidfuzz.py:103-104), and the matcher can be
+reused for a two-list call after a self-match (`equal_lists` is per call)."""
+from typing import Callable, List, Union
+
+import numpy as np
+import pandas as pd
+
+from ._base import BaseMatcher
+from .. import editdist
+
+_NAMES = {"ratio": "ratio", "levenshtein": "norm_lev", "norm_lev": "norm_lev", "normalized_similarity": "norm_lev",
+          "normalized_levenshtein": "norm_lev"}
+
+
+def _resolve_scorer(scorer) -> str:
+    if scorer is None:
+        return "ratio"
+    if isinstance(scorer, str):
+        key = scorer.lower()
+    else:
+        key = getattr(scorer, "__name__", "")
+    if key in _NAMES:
+        return _NAMES[key]
+    raise NotImplementedError(f"scorer {scorer!r} has no GPU implementation (supported: 'ratio', 'levenshtein'); "
+                              "polyfuzz_b200 has no CPU fallback")
+
+
+class RapidFuzz(BaseMatcher):
+    """Edit-distance matcher (GPU).  Arguments as in the reference: n_jobs (accepted, ignored -- the GPU
+    scores all pairs in one launch), score_cutoff in [0,1], scorer (default "ratio"; the reference
+    defaults to fuzz.WRatio, which is not on the GPU path), model_id."""
+
+    def __init__(self, n_jobs: int = 1, score_cutoff: float = 0, scorer: Union[str, Callable] = "ratio", model_id: str = None):
+        super().__init__(model_id)
+        self.type = "EditDistance"
+        self.score_cutoff = score_cutoff * 100
+        self.scorer = scorer
+        self._metric = _resolve_scorer(scorer)
+        self.equal_lists = False
+        self.n_jobs = n_jobs
+
+    def match(self, from_list: List[str], to_list: List[str] = None, **kwargs) -> pd.DataFrame:
+        """(from, best to, score/100); no candidate with score >= score_cutoff -> (from, None, 0.0)
+        (polyfuzz/models/_rapidfuzz.py:106-113)."""
+        self_match = to_list is None
+        targets = from_list if self_match else to_list
+        scale = 100.0 if self._metric == "ratio" else 1.0
+        cutoff = self.score_cutoff if self._metric == "ratio" else self.score_cutoff / 100.0
+        idx, score, _ = editdist.edit_argbest(from_list, targets, self._metric, cutoff, exclude_self=self_match)
+        idx = idx.cpu().numpy(); score = score.cpu().numpy() / scale
+        to_arr = np.empty(len(targets) + 1, dtype=object); to_arr[:-1] = targets; to_arr[-1] = None
+        sel = np.where(idx >= 0, idx, len(targets))
+        return pd.DataFrame({"From": pd.Series(list(from_list), dtype=object), "To": pd.Series(to_arr[sel], dtype=object),
+                             "Similarity": np.where(idx >= 0, score, 0.0)})
+
+
+class EditDistance(BaseMatcher):
+    """Edit-distance matcher with the reference's EditDistance surface (n_jobs, scorer, model_id, normalize):
+    Similarity is the scorer's raw value (fuzz.ratio: 0..100) of the best to-string, min-max normalised
+    over the column when `normalize` (polyfuzz/models/_distance.py:83-86)."""
+
+    def __init__(self, n_jobs: int = 1, scorer: Union[str, Callable] = "ratio", model_id: str = None, normalize: bool = True):
+        super().__init__(model_id)
+        self.type = "EditDistance"
+        self.scorer = scorer
+        self._metric = _resolve_scorer(scorer)
+        self.normalize = normalize
+        self.equal_lists = False
+        self.n_jobs = n_jobs
+
+    def match(self, from_list: List[str], to_list: List[str] = None, **kwargs) -> pd.DataFrame:
+        self_match = to_list is None
+        targets = from_list if self_match else to_list
+        if len(targets) - (1 if self_match else 0) < 1:
+            raise ValueError("attempt to get argmax of an empty sequence")         # np.argmax on [] in the reference
+        idx, score, _ = editdist.edit_argbest(from_list, targets, self._metric, float("-inf"), exclude_self=self_match)
+        idx = idx.cpu().numpy(); score = score.cpu().numpy()
+        to_arr = np.empty(len(targets), dtype=object); to_arr[:] = targets
+        matches = pd.DataFrame({"From": pd.Series(list(from_list), dtype=object), "To": pd.Series(to_arr[idx], dtype=object),
+                                "Similarity": score})
+        if self.normalize:
+            s = matches["Similarity"]
+            matches["Similarity"] = (s - s.min()) / (s.max() - s.min())
+        return matches
