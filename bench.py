@@ -301,7 +301,7 @@ def run_b200(args):
         except Exception:
             traffic = None
     achieved = b_alg / (k2_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "pfz::spcos_topk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "pfz::spcos_dense_kernel (K2)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_alg, "postings_per_launch": P, "kernel_ms_avg": k2_avg_ms,
                 "kernel_share_of_step": k2_avg_ms / ms_per_step,
