@@ -177,9 +177,23 @@ int pfz_lev_merge(const int32_t *part_idx, const double *part_score, const int32
                   int32_t n_from, int32_t *best_idx, double *best_score, int32_t *best_dist, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
- * End-to-end convenience entry with HOST buffers (what a foreign-language binding would call):
- * self- or two-list TF-IDF match, H2D + K1 + K2 + D2H inside.  See INTEGRATION.md.
+ * K4  dense cosine top-k for pre-computed embeddings (bf16 tcgen05 GEMM fed by TMA, top-k fused into the
+ * epilogue).  Replaces the dense branch polyfuzz/models/_utils.py:94-102 (sklearn cosine_similarity +
+ * argsort) reached from polyfuzz/models/_embeddings.py:127-131.
  * ---------------------------------------------------------------------------------------------- */
+
+/* rows (float32 or float64, row pitch ld elements) -> bf16 [n_rows][d_pad], optionally l2-normalised
+ * (sk:metrics/pairwise.py:1744-1750 normalises both sides); columns d..d_pad are zero.  d_pad % 8 == 0.  */
+int pfz_rows_to_bf16(const void *x, int32_t is_f64, int64_t ld, int32_t n_rows, int32_t d, int32_t d_pad,
+                     int32_t normalize, void *out_bf16, void *stream);
+
+/* top-k of X * Y^T.  x_bf16 [n_from][d], y_bf16 [n_to][d] row-major bf16, d % 8 == 0, 16-byte aligned.
+ *   candidate iff score > min_similarity (strict) and not the diagonal (self_match); key (score desc,
+ *   index asc) on the fp32 accumulator values; k <= 32; partial lists [n_splits][n_from][k] (idx int32
+ *   global, score as float64) -> pfz_topk_merge when n_splits > 1.                                     */
+int pfz_dense_cos_topk(const void *x_bf16, const void *y_bf16, int32_t n_from, int32_t n_to, int32_t d, int32_t k,
+                       double min_similarity, int32_t self_match, int64_t from_index_base, int64_t to_index_base,
+                       int32_t n_splits, int32_t *top_idx, double *top_val, void *stream);
 
 #ifdef __cplusplus
 }

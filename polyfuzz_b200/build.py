@@ -40,7 +40,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + sources() + ["-lcuda"]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + sources()
     env = dict(os.environ)
     # the image's CC wrapper lacks OpenMP specs; nvcc only needs a plain host g++
     env.pop("CC", None); env.pop("CXX", None)

@@ -1,0 +1,50 @@
+"""Embeddings matcher -- drop-in for the pre-computed-vector path of polyfuzz.models.Embeddings
+(polyfuzz/models/_embeddings.py:87-135): dense cosine top-n on the tensor cores (K4).  The language-model
+embedders themselves (`_embed`, Flair / SBERT / ...) are out of scope: supply
+`embeddings_from` / `embeddings_to`, or an `embedding_method` callable `list[str] -> ndarray`."""
+from typing import Callable, List
+
+import numpy as np
+import pandas as pd
+
+from ._base import BaseMatcher
+from ._utils import assemble_matches, clip_top_n
+from .. import dense
+
+
+class Embeddings(BaseMatcher):
+    def __init__(self, embedding_method: Callable = None, min_similarity: float = 0.75, top_n: int = 1,
+                 cosine_method: str = "sparse", model_id: str = None):
+        super().__init__(model_id)
+        self.type = "Embeddings"
+        self.embedding_method = embedding_method
+        self.min_similarity = min_similarity
+        self.top_n = top_n
+        self.cosine_method = cosine_method
+        self.embeddings_to = None
+
+    def _embed(self, strings):
+        if not callable(self.embedding_method):
+            raise NotImplementedError("language-model embedders are out of scope here: pass embeddings_from / embeddings_to "
+                                      "or an embedding_method callable (list[str] -> ndarray)")
+        return np.asarray(self.embedding_method(strings))
+
+    def match(self, from_list: List[str], to_list: List[str] = None, embeddings_from: np.ndarray = None,
+              embeddings_to: np.ndarray = None, re_train: bool = True) -> pd.DataFrame:
+        """polyfuzz/models/_embeddings.py:87-135.  Rows are l2-normalised (as the reference's sklearn branch does,
+        sk:metrics/pairwise.py:1744-1750; identical to its sparse branch for unit-norm inputs)."""
+        if not isinstance(embeddings_from, np.ndarray):
+            embeddings_from = self._embed(from_list)
+        if not isinstance(embeddings_to, np.ndarray):
+            if not re_train:
+                embeddings_to = self.embeddings_to
+            elif to_list is None:
+                embeddings_to = embeddings_from
+            else:
+                embeddings_to = self._embed(to_list)
+        top_n = clip_top_n(self.top_n, to_list)
+        x, _ = dense.to_bf16_rows(embeddings_from, normalize=True)
+        y = x if embeddings_to is embeddings_from else dense.to_bf16_rows(embeddings_to, normalize=True)[0]
+        idx, val = dense.dense_topk(x, y, top_n, self.min_similarity, self_match=to_list is None)
+        self.embeddings_to = embeddings_to
+        return assemble_matches(from_list, to_list, idx.cpu().numpy(), val.cpu().numpy())
