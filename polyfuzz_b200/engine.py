@@ -37,15 +37,51 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+class _PinnedPool:
+    """Reusable pinned staging buffers (cudaHostAlloc per call costs more than the copy for MB-sized
+    inputs).  A buffer is handed out again only after the H2D copy that used it has completed."""
+
+    def __init__(self):
+        self.free = []          # [(tensor uint8, event or None)]
+
+    def take(self, nbytes):
+        best = None
+        for i, (buf, ev) in enumerate(self.free):
+            if buf.numel() >= nbytes and (best is None or buf.numel() < self.free[best][0].numel()):
+                best = i
+        if best is not None:
+            buf, ev = self.free.pop(best)
+            if ev is not None:
+                ev.synchronize()
+            return buf
+        size = max(1 << 16, 1 << int(nbytes - 1).bit_length())
+        return torch.empty(size, dtype=torch.uint8).pin_memory()
+
+    def give(self, buf, ev):
+        if len(self.free) < 16:
+            self.free.append((buf, ev))
+
+
+_PINNED = _PinnedPool()
+
+
 def _to_dev(arr, dtype=None):
-    """numpy -> device tensor via pinned staging (async H2D on the current stream)."""
+    """numpy -> device tensor via pooled pinned staging (async H2D on the current stream)."""
     dev = _dev()                                           # fail loudly without a GPU, before any work
-    t = torch.from_numpy(np.ascontiguousarray(arr))
+    arr = np.ascontiguousarray(arr)
+    t = torch.from_numpy(arr)
     if dtype is not None:
         t = t.view(dtype)
     if t.numel() == 0:
         return torch.empty(0, dtype=t.dtype, device=dev)
-    return t.pin_memory().to(dev, non_blocking=True)
+    nbytes = arr.nbytes
+    stage = _PINNED.take(nbytes)
+    stage[:nbytes].copy_(torch.from_numpy(arr.reshape(-1).view(np.uint8)))
+    out = torch.empty(t.shape, dtype=t.dtype, device=dev)
+    out.view(torch.uint8).reshape(-1).copy_(stage[:nbytes], non_blocking=True)
+    ev = torch.cuda.Event(); ev.record()
+    _PINNED.give(stage, ev)
+    return out
 
 
 def _ws(nbytes):

@@ -1,7 +1,12 @@
-"""The plugin type.  When the reference package is importable its own `polyfuzz.models.BaseMatcher`
-is used, so the B200 matchers ARE reference plugins (isinstance checks in polyfuzz/polyfuzz.py:127-151
-pass and `PolyFuzz(method=TFIDF(...))` works unmodified).  Otherwise an identical ABC is defined
-(mirror of polyfuzz/models/_base.py:6-31: abstract match(), attributes model_id and type)."""
+"""The plugin type.
+
+When the reference package is importable at import time its own `polyfuzz.models.BaseMatcher` is the base
+class, so the B200 matchers ARE reference plugins.  Otherwise an identical ABC is defined here (mirror of
+polyfuzz/models/_base.py:6-31: abstract match(), attributes model_id and type) and, should `polyfuzz`
+become importable later in the process, every matcher class is registered with the reference's ABC as a
+virtual subclass -- either way `isinstance(m, polyfuzz.models.BaseMatcher)` holds and
+`PolyFuzz(method=TFIDF(...))` (polyfuzz/polyfuzz.py:127-151) works unmodified."""
+import sys
 from abc import ABC, abstractmethod
 from typing import List
 
@@ -11,7 +16,7 @@ try:                                                    # pragma: no cover - dep
     from polyfuzz.models import BaseMatcher as _RefBaseMatcher
     BaseMatcher = _RefBaseMatcher
     REFERENCE_BASE = True
-except Exception:                                       # reference not installed: same contract, own ABC
+except Exception:                                       # reference not importable now: same contract, own ABC
     REFERENCE_BASE = False
 
     class BaseMatcher(ABC):
@@ -20,8 +25,24 @@ except Exception:                                       # reference not installe
         def __init__(self, model_id: str = "Model 0"):
             self.model_id = model_id
             self.type = "Base Model"
+            register_with_reference(type(self))
 
         @abstractmethod
         def match(self, from_list: List[str], to_list: List[str] = None, **kwargs) -> pd.DataFrame:
             """Returns a DataFrame with columns From, To, Similarity (one row per from_list element)."""
             raise NotImplementedError()
+
+_REGISTERED = set()
+
+
+def register_with_reference(cls) -> bool:
+    """Register `cls` as a virtual subclass of the reference's BaseMatcher if `polyfuzz` is loaded."""
+    if REFERENCE_BASE or cls in _REGISTERED:
+        return True
+    mod = sys.modules.get("polyfuzz.models")
+    ref = getattr(mod, "BaseMatcher", None) if mod is not None else None
+    if ref is None:
+        return False
+    ref.register(cls)
+    _REGISTERED.add(cls)
+    return True

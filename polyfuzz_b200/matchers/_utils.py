@@ -42,7 +42,19 @@ def _str_dtype():
     return None
 
 
-def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarray) -> pd.DataFrame:
+def prepare_strings(from_list, to_list):
+    """Arrow arrays of the string lists (the only per-string host work of the assembly); callers build them
+    while the GPU is still scoring and pass them to assemble_matches(prepared=...)."""
+    dt = _str_dtype()
+    if dt is None or len(from_list) == 0:
+        return None
+    same = to_list is None or to_list is from_list
+    to_pa = pa.array(from_list if same else to_list, type=pa.large_string())
+    from_pa = to_pa if same else pa.array(from_list, type=pa.large_string())
+    return from_pa, to_pa
+
+
+def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarray, prepared=None) -> pd.DataFrame:
     """top_idx int32[n,k] (global to-index, -1 = none), top_val float64[n,k] (unrounded scores).
     Columns From, To, Similarity, To_2, Similarity_2, ... ; similarities rounded to 3 decimals
     (_utils.py:102); Similarity < 0.001 -> 0.0 and To -> None (_utils.py:119-123)."""
@@ -59,8 +71,7 @@ def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarra
     cols = {}
     if dt is not None and n > 0:
         AT = dt.construct_array_type()
-        to_pa = pa.array(to_list, type=pa.large_string())
-        from_pa = to_pa if same else pa.array(from_list, type=pa.large_string())
+        from_pa, to_pa = prepared if prepared is not None else prepare_strings(from_list, None if same else to_list)
         cols["From"] = pd.Series(AT(from_pa, dtype=dt), copy=False)
 
         def gather(r):

@@ -250,3 +250,25 @@ def test_every_row_shares_many_heavy_terms(pf, variant, monkeypatch):
     oi, ov = onative.spdot_topn(a, a, k, 0.0, self_match=True, n_threads=8)
     np.testing.assert_array_equal(idx.cpu().numpy(), oi)
     np.testing.assert_array_equal(val.cpu().numpy(), ov)
+
+
+def test_shard_emulation_equals_unsharded(pf):
+    """Multi-GPU result = merge of per-shard top-k with global indices (emulated sequentially on one GPU:
+    same vectoriser state on every 'rank', one index per to-block, pfz_topk_merge)."""
+    import torch
+    polyfuzz_b200, engine = pf
+    from polyfuzz_b200 import synth
+    from polyfuzz_b200.distributed import shard_bounds
+    to = synth.company_names(5000, seed=21); frm = synth.company_names(1200, seed=22)
+    v = engine.NgramTfidf((3, 3), True, True)
+    rows_to, rows_from = v.fit_rows([to, frm])
+    csr_to, csr_from = v.emit(rows_to), v.emit(rows_from)
+    full_i, full_v = engine.spcos_topk(csr_from, engine.SparseIndex(csr_to, variant="dense"), 10, 0.0)
+    parts_i, parts_v = [], []
+    for r in range(3):
+        lo, hi = shard_bounds(len(to), 3, r)
+        blk = v.transform(to[lo:hi])
+        i_, v_ = engine.spcos_topk(csr_from, engine.SparseIndex(blk, variant="dense"), 10, 0.0, to_index_base=lo)
+        parts_i.append(i_); parts_v.append(v_)
+    mi, mv = engine.topk_merge(torch.stack(parts_i), torch.stack(parts_v), 10)
+    assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
