@@ -119,7 +119,8 @@ int64_t pfz_scan_ws_bytes(int64_t n);
 #define PFZ_INDEX_BANK_ORDER 1   /* arrange each segment so that 16 consecutive postings hit distinct smem banks */
 int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double *data, int32_t n_rows,
                     int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t flags,
-                    int32_t *seg, uint16_t *post_idx, double *post_val, void *ws, void *stream);
+                    int32_t *seg, uint16_t *post_idx, double *post_val, float *post_val32 /* may be NULL */,
+                    void *ws, void *stream);
 
 /* top-k of (from CSR) x (to inverted index).
  *   k <= 32.  n_splits > 1 splits the to-tiles over blockIdx.y and writes partial lists
@@ -129,12 +130,19 @@ int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double 
  *   AFTER (excl_val[i], excl_idx[i]) are considered (used to page through top_n > 32).
  *   row_counter: int32[n_splits] on device, zeroed by the callee (dynamic row scheduling).
  *   variant: PFZ_K2_LIST  -- touched-list selection, work ~ postings (sparse inputs, e.g. uniform text)
- *            PFZ_K2_DENSE -- threshold-crossing bitmap + dense accumulator clear (rows that touch a
- *                            sizeable fraction of every tile, e.g. company names); same results.       */
+ *            PFZ_K2_DENSE -- threshold-crossing flags + dense accumulator clear (rows that touch a
+ *                            sizeable fraction of every tile, e.g. company names); same results.
+ *            PFZ_K2_DENSE32 -- like DENSE with an fp32 FILTER: fp32 weights (post_val32) and fp32 shared-memory
+ *                            sums decide which to-rows could rank before the k-th key (margin 2e-5); each of
+ *                            those is re-scored exactly from the two CSR rows (b_* = the to-matrix CSR the index
+ *                            was built from), so indices and scores are bit-identical to the other variants.
+ *                            Requires l2-normalised rows with positive weights (TF-IDF).                      */
 #define PFZ_K2_LIST  1
 #define PFZ_K2_DENSE 2
+#define PFZ_K2_DENSE32 3
 int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from,
                    const int32_t *seg, const uint16_t *post_idx, const double *post_val,
+                   const float *post_val32, const int32_t *b_indptr, const int32_t *b_indices, const double *b_data,
                    int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to,
                    int32_t k, double min_similarity, int32_t self_match,
                    int64_t from_index_base, int64_t to_index_base, int32_t n_splits,

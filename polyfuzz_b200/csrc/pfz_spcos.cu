@@ -94,6 +94,11 @@ __global__ void __launch_bounds__(128) index_bank_order_kernel(const int32_t *__
     }
 }
 
+__global__ void to_f32_kernel(const double *__restrict__ x, int64_t n_minus, const int32_t *__restrict__ n_ptr, float *__restrict__ y) {
+    const int64_t n = n_ptr ? (int64_t)*n_ptr : n_minus;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = (float)x[i];
+}
+
 // ---- K2 --------------------------------------------------------------------------------------
 // ranking key: (score desc, idx asc); "a before b"
 __device__ __forceinline__ bool key_before(double sa, int ia, double sb, int ib) {
@@ -103,6 +108,7 @@ __device__ __forceinline__ bool key_before(double sa, int ia, double sb, int ib)
 struct SpcosParams {
     const int32_t *a_indptr; const int32_t *a_indices; const double *a_data; int n_from;
     const int32_t *seg; const uint16_t *post_idx; const double *post_val;
+    const float *post_val32; const int32_t *b_indptr; const int32_t *b_indices; const double *b_data;   // mixed-precision variant
     int n_vocab, tile, n_tiles, n_to;
     int k; double min_sim; int self_match; int64_t from_base, to_base;
     int n_splits; const double *excl_val; const int32_t *excl_idx;
@@ -275,26 +281,79 @@ __device__ __forceinline__ void flag_if_crossed(unsigned flag_addr, double old, 
 }
 
 
-template <int WARPS, int D>
+
+// ---- mixed-precision filter (PFZ_K2_DENSE32) --------------------------------------------------------
+// The accumulators, the posting weights and the from-row weights are fp32: half the shared-memory and L2
+// bytes per posting.  The fp32 sums only FILTER: a to-row is flagged when its sum first passes
+// thr - MARGIN, and every flagged row is re-scored exactly -- fp64, ascending term order, products rounded
+// before the add -- by merging the two CSR rows, so the ranking and the returned scores are the canonical
+// ones bit for bit.  |fp32 sum - exact| <= ~70 * 2^-24 + 3 * 2^-24 < 5e-6 for l2-normalised rows (all
+// terms positive, exact sum <= 1), MARGIN = 2e-5.
+constexpr double K2_MARGIN = 2e-5;
+__device__ __forceinline__ void lds_item32(unsigned a, unsigned &off, int &cnt, float &v) {
+    unsigned vv, pad;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(off), "=r"(cnt), "=r"(vv), "=r"(pad) : "r"(a) : "memory");
+    v = __uint_as_float(vv);
+}
+__device__ __forceinline__ void ldg_posting32(const uint16_t *pi, const float *pv, int lane, int cnt, unsigned dummy, unsigned &jl, float &w) {
+    asm volatile("{ .reg .pred p; setp.lt.s32 p, %2, %3; mov.u32 %0, %4; mov.f32 %1, 0f00000000;\n\t"
+                 "@p ld.global.nc.u16 %0, [%5]; @p ld.global.nc.f32 %1, [%6]; }"
+                 : "=&r"(jl), "=&f"(w) : "r"(lane), "r"(cnt), "r"(dummy), "l"(pi), "l"(pv) : "memory");
+}
+__device__ __forceinline__ void rmw_posting32(unsigned acc_s, unsigned flags_s, unsigned row, unsigned dummy, float v, float w, float thr,
+                                              unsigned &any) {
+    asm volatile("{ .reg .pred p, q, r; .reg .f32 o, n; .reg .b16 one; .reg .u32 a, f;\n\t"
+                 "setp.ne.u32 p, %3, %4; mov.f32 o, 0f00000000;\n\t"
+                 "shl.b32 a, %3, 2; add.u32 a, a, %1; add.u32 f, %2, %3;\n\t"
+                 "@p ld.shared.f32 o, [a];\n\t"
+                 "fma.rn.f32 n, %5, %6, o;\n\t"
+                 "@p st.shared.f32 [a], n;\n\t"
+                 "setp.gt.f32 q, o, %7; setp.gt.and.f32 r, n, %7, !q; mov.b16 one, 1;\n\t"
+                 "@r st.shared.u8 [f], one; selp.u32 %0, 1, %0, r; }"
+                 : "+r"(any) : "r"(acc_s), "r"(flags_s), "r"(row), "r"(dummy), "f"(v), "f"(w), "f"(thr) : "memory");
+}
+// canonical score of (from-row a, to-row b): common terms in ascending order, product rounded, then added
+__device__ __forceinline__ double exact_dot(const int32_t *__restrict__ ai, const double *__restrict__ av, int an,
+                                            const int32_t *__restrict__ bi, const double *__restrict__ bv, int bn) {
+    double s = 0.0;
+    int p = 0, q = 0;
+    while (p < an && q < bn) {
+        const int ca = ai[p], cb = bi[q];
+        if (ca == cb) { s = __dadd_rn(s, __dmul_rn(av[p], bv[q])); ++p; ++q; }
+        else if (ca < cb) ++p; else ++q;
+    }
+    return s;
+}
+// largest float not above x (x >= 0)
+__device__ __forceinline__ float float_floor(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = __uint_as_float(__float_as_uint(f) - 1u);
+    return f;
+}
+
+template <int WARPS, int D, bool APPROX>
 __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosParams P) {
     extern __shared__ __align__(16) unsigned char dyn[];
     const int lane = lane_id();
     const int w = threadIdx.x >> 5;
     const int T = P.tile;
     const int max_items = (T >> 5) + 32 + 2 * D;
-    // per-warp arena: acc double[T + 2] (row T = dummy for idle lanes) | items WorkItem[max_items] | flags uint8[T + 16]
-    const size_t arena = (size_t)(T + 2) * 8 + (size_t)max_items * sizeof(WorkItem) + (size_t)T + 16;
+    // per-warp arena: acc (double | float)[T + 4] | items WorkItem[max_items] | flags uint8[T + 16] | cand int[64]
+    constexpr int ES = APPROX ? 4 : 8;
+    const size_t arena = (size_t)(T + 4) * ES + (size_t)max_items * sizeof(WorkItem) + (size_t)T + 16 + 256;
     unsigned char *base = dyn + (size_t)w * ((arena + 15) & ~(size_t)15);
     double *acc = reinterpret_cast<double *>(base);
-    WorkItem *items = reinterpret_cast<WorkItem *>(base + (size_t)(T + 2) * 8);
-    unsigned char *flags = base + (size_t)(T + 2) * 8 + (size_t)max_items * sizeof(WorkItem);
-    for (int q = lane; q < T + 2; q += 32) acc[q] = 0.0;
+    WorkItem *items = reinterpret_cast<WorkItem *>(base + (size_t)(T + 4) * ES);
+    unsigned char *flags = base + (size_t)(T + 4) * ES + (size_t)max_items * sizeof(WorkItem);
+    int *cand = reinterpret_cast<int *>(flags + T + 16);           // mixed precision: flagged to-rows awaiting exact re-scoring
+    for (int q = lane; q < (T + 4) * ES / 4; q += 32) reinterpret_cast<unsigned *>(base)[q] = 0u;
     for (int q = lane; q < T + 16; q += 32) flags[q] = 0;
     __syncwarp();
     const unsigned acc_s = smem_u32(acc), items_s = smem_u32(items), flags_s = smem_u32(flags);
     const uint16_t *pidx_lane = P.post_idx + lane;
     const double *pval_lane = P.post_val + lane;
-    asm volatile("" : "+l"(pidx_lane), "+l"(pval_lane));          // keep the two base pointers in registers
+    const float *pval32_lane = P.post_val32 + lane;
+    asm volatile("" : "+l"(pidx_lane), "+l"(pval_lane), "+l"(pval32_lane));   // keep the base pointers in registers
     const int32_t *__restrict__ seg = P.seg;
     const int n_tiles = P.n_tiles, K = P.k;
 
@@ -319,6 +378,7 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
         // not full (strict; untouched sums are 0) and the double just below kv once it is (inclusive: ties are
         // settled on the index at the end of the unit)
         double thr = fmax(P.min_sim, 0.0);
+        float thr32 = float_floor(fmax(P.min_sim - K2_MARGIN, 0.0));
         double xv = 0.0; int xi = -1; bool has_x = false;
         if (P.excl_val) { xv = P.excl_val[i]; xi = P.excl_idx[i]; has_x = xi >= 0; }
         const int64_t self_j = P.from_base + i - P.to_base;
@@ -326,6 +386,39 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
         // near the row itself, so the k-th key is high from the first unit on (order does not affect results)
         int first_tau = tau_lo;
         if (P.self_match && self_j >= (int64_t)tau_lo * T && self_j < (int64_t)tau_hi * T) first_tau = (int)(self_j / T);
+
+        // exact scoring + insertion of up to 32 candidates (one per lane); mixed precision batches its flagged rows
+        // across units so that each round of dependent CSR loads serves a full warp
+        int ncand = 0;
+        auto score_round = [&](int n_round) {
+            double sc = 0.0; int j = -1; bool cnd = false;
+            if (lane < n_round) {
+                const int jloc = cand[lane];
+                const int b0 = P.b_indptr[jloc];
+                sc = exact_dot(P.a_indices + a0, P.a_data + a0, m, P.b_indices + b0, P.b_data + b0, P.b_indptr[jloc + 1] - b0);
+                j = (int)(P.to_base + jloc);
+                cnd = key_before(sc, j, kv, ki);
+                if (P.self_match && (int64_t)jloc == self_j) cnd = false;
+                if (has_x && !key_before(xv, xi, sc, j)) cnd = false;
+            }
+            unsigned cm = __ballot_sync(FULL, cnd);
+            while (cm) {
+                const int src = __ffs(cm) - 1;
+                const double cs = shfl_d(sc, src);
+                const int cjx = __shfl_sync(FULL, j, src);
+                const bool stays = (lane < K) && key_before(tv, ti, cs, cjx);
+                const int pos = __popc(__ballot_sync(FULL, stays));
+                const double uv = __shfl_up_sync(FULL, tv, 1);
+                const int ui = __shfl_up_sync(FULL, ti, 1);
+                if (lane > pos) { tv = uv; ti = ui; }
+                else if (lane == pos) { tv = cs; ti = cjx; }
+                kv = shfl_d(tv, K - 1);
+                ki = __shfl_sync(FULL, ti, K - 1);
+                cnd = cnd && lane != src && key_before(sc, j, kv, ki);
+                cm = __ballot_sync(FULL, cnd);
+            }
+            thr32 = float_floor(fmax(kv - K2_MARGIN, 0.0));
+        };
 
         // rows with <= 32 terms (the common case) keep their terms in registers across tiles
         int t_reg = 0; double v_reg = 0.0; int prev_end = 0;
@@ -362,7 +455,8 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                     const int N = endv - start;
                     if (inb) {
                         int o = incl - nch - start, so = s, rem = len;
-                        while (rem > 0) { WorkItem wi; wi.off = so; wi.cnt = rem; wi.v = v; items[o] = wi; ++o; so += 32; rem -= 32; }
+                        const double vitem = APPROX ? __hiloint2double(0, (int)__float_as_uint((float)v)) : v;   // fp32 weight in the low word
+                        while (rem > 0) { WorkItem wi; wi.off = so; wi.cnt = rem; wi.v = vitem; items[o] = wi; ++o; so += 32; rem -= 32; }
                     }
                     if (lane < 2 * D) { WorkItem wi; wi.off = 0; wi.cnt = 0; wi.v = 0.0; items[N + lane] = wi; }   // padding
                     __syncwarp();
@@ -370,23 +464,44 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                     // item b+d+D (padding items have cnt = 0, so no guard is needed).  Idle lanes add 0 to the dummy
                     // row T.  No warp barrier between items: the loop body has no branch, the warp stays converged
                     // and its shared-memory instructions complete in program order.
-                    unsigned rj[D]; double rw[D], rv[D];
-#pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        unsigned off; int cnt;
-                        lds_item(items_s + d * 16, off, cnt, rv[d]);
-                        ldg_posting(pidx_lane + off, pval_lane + off, lane, cnt, (unsigned)T, rj[d], rw[d]);
-                    }
-                    unsigned it_s = items_s + D * 16;
-                    for (int b = 0; b < N; b += D) {
+                    if (!APPROX) {
+                        unsigned rj[D]; double rw[D], rv[D];
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
-                            rmw_posting(acc_s, flags_s, rj[d], (unsigned)T, rv[d], rw[d], thr, crossed_any);
                             unsigned off; int cnt;
-                            lds_item(it_s + d * 16, off, cnt, rv[d]);
+                            lds_item(items_s + d * 16, off, cnt, rv[d]);
                             ldg_posting(pidx_lane + off, pval_lane + off, lane, cnt, (unsigned)T, rj[d], rw[d]);
                         }
-                        it_s += D * 16;
+                        unsigned it_s = items_s + D * 16;
+                        for (int b = 0; b < N; b += D) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d) {
+                                rmw_posting(acc_s, flags_s, rj[d], (unsigned)T, rv[d], rw[d], thr, crossed_any);
+                                unsigned off; int cnt;
+                                lds_item(it_s + d * 16, off, cnt, rv[d]);
+                                ldg_posting(pidx_lane + off, pval_lane + off, lane, cnt, (unsigned)T, rj[d], rw[d]);
+                            }
+                            it_s += D * 16;
+                        }
+                    } else {
+                        unsigned rj[D]; float rw[D], rv[D];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            unsigned off; int cnt;
+                            lds_item32(items_s + d * 16, off, cnt, rv[d]);
+                            ldg_posting32(pidx_lane + off, pval32_lane + off, lane, cnt, (unsigned)T, rj[d], rw[d]);
+                        }
+                        unsigned it_s = items_s + D * 16;
+                        for (int b = 0; b < N; b += D) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d) {
+                                rmw_posting32(acc_s, flags_s, rj[d], (unsigned)T, rv[d], rw[d], thr32, crossed_any);
+                                unsigned off; int cnt;
+                                lds_item32(it_s + d * 16, off, cnt, rv[d]);
+                                ldg_posting32(pidx_lane + off, pval32_lane + off, lane, cnt, (unsigned)T, rj[d], rw[d]);
+                            }
+                            it_s += D * 16;
+                        }
                     }
                     __syncwarp();
                     start = endv;
@@ -395,23 +510,89 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
             if (!any_post) continue;
             // candidates: flagged to-rows -> final sums -> exact key test -> insertion
             if (__any_sync(FULL, crossed_any != 0u)) {
+                // Mixed precision only: when many rows are flagged (the first units of a from-row, before the
+                // k-th key has risen) re-scoring all of them exactly would dominate.  Pass A finds the k-th largest
+                // fp32 sum among the flagged rows (shared memory only); a row can reach the unit's exact top-k only
+                // if its fp32 sum is within MARGIN of that value, so pass B re-scores just those.
+                float gate = thr32;
+                if (APPROX) {
+                    int nflag = 0;
+                    for (int w0 = 0; w0 < T; w0 += 128) {
+                        const int q4 = w0 + lane * 4;
+                        if (q4 < T) { const unsigned bits = *reinterpret_cast<const unsigned *>(flags + q4); nflag += __popc(bits & 0x01010101u); }
+                    }
+                    nflag = __reduce_add_sync(FULL, nflag);
+                    if (nflag > 2 * K + 32 && !has_x) {              // (paging excludes rows by exact key: no pre-selection then)
+                        const float *acc32 = reinterpret_cast<const float *>(acc);
+                        float lv = -1.f;                                  // lane r: r-th largest fp32 sum so far (r < K)
+                        float kth = -1.f;
+                        for (int w0 = 0; w0 < T; w0 += 128) {
+                            const int q4 = w0 + lane * 4;
+                            unsigned bits = (q4 < T) ? *reinterpret_cast<const unsigned *>(flags + q4) : 0u;
+                            while (__ballot_sync(FULL, bits != 0u)) {
+                                float a = -2.f;
+                                if (bits) {
+                                    const int b8 = (__ffs(bits) - 1) >> 3; bits &= ~(0xffu << (b8 * 8)); a = acc32[q4 + b8];
+                                    if (P.self_match && (int64_t)(tau * T + q4 + b8) == self_j) a = -2.f;     // the diagonal never competes
+                                }
+                                unsigned cm = __ballot_sync(FULL, a > kth);
+                                while (cm) {
+                                    const int src = __ffs(cm) - 1;
+                                    const float ca = __shfl_sync(FULL, a, src);
+                                    const int pos = __popc(__ballot_sync(FULL, (lane < K) && lv >= ca));
+                                    const float up = __shfl_up_sync(FULL, lv, 1);
+                                    if (lane > pos) lv = up; else if (lane == pos) lv = ca;
+                                    kth = __shfl_sync(FULL, lv, K - 1);
+                                    a = (lane == src) ? -2.f : a;
+                                    cm = __ballot_sync(FULL, a > kth);
+                                }
+                            }
+                        }
+                        gate = fmaxf(gate, float_floor(fmax((double)kth - K2_MARGIN, 0.0)));
+                    }
+                }
                 for (int w0 = 0; w0 < T; w0 += 128) {               // 4 flag bytes per lane per step
                     unsigned bits = 0u;
                     const int q4 = w0 + lane * 4;
                     if (q4 < T) { bits = *reinterpret_cast<const unsigned *>(flags + q4); if (bits) *reinterpret_cast<unsigned *>(flags + q4) = 0u; }
                     while (__ballot_sync(FULL, bits != 0u)) {
-                        double sc = 0.0; int j = -1; bool cand = false;
+                        if (APPROX) {
+                            bool take = false; int jloc = 0;
+                            if (bits) {
+                                const int b8 = (__ffs(bits) - 1) >> 3; bits &= ~(0xffu << (b8 * 8));
+                                const int jl = q4 + b8;
+                                jloc = tau * T + jl;
+                                take = reinterpret_cast<const float *>(acc)[jl] > gate;
+                            }
+                            const unsigned tm = __ballot_sync(FULL, take);
+                            if (take) cand[ncand + __popc(tm & ((1u << lane) - 1u))] = jloc;
+                            ncand += __popc(tm);
+                            __syncwarp();
+                            if (ncand >= 32) {                        // a full warp of candidates: score them now
+                                score_round(32);
+                                __syncwarp();
+                                const int rest = ncand - 32;
+                                int mv = 0;
+                                if (lane < rest) mv = cand[32 + lane];
+                                __syncwarp();
+                                if (lane < rest) cand[lane] = mv;
+                                ncand = rest;
+                                __syncwarp();
+                            }
+                            continue;
+                        }
+                        double sc = 0.0; int j = -1; bool cnd = false;
                         if (bits) {
                             const int b8 = (__ffs(bits) - 1) >> 3; bits &= ~(0xffu << (b8 * 8));
                             const int jl = q4 + b8;
-                            sc = acc[jl];
                             const int jloc = tau * T + jl;
+                            sc = acc[jl];
                             j = (int)(P.to_base + jloc);
-                            cand = key_before(sc, j, kv, ki);
-                            if (P.self_match && (int64_t)jloc == self_j) cand = false;
-                            if (has_x && !key_before(xv, xi, sc, j)) cand = false;
+                            cnd = key_before(sc, j, kv, ki);
+                            if (P.self_match && (int64_t)jloc == self_j) cnd = false;
+                            if (has_x && !key_before(xv, xi, sc, j)) cnd = false;
                         }
-                        unsigned cm = __ballot_sync(FULL, cand);
+                        unsigned cm = __ballot_sync(FULL, cnd);
                         while (cm) {
                             const int src = __ffs(cm) - 1;
                             const double cs = shfl_d(sc, src);
@@ -425,22 +606,24 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                             kv = shfl_d(tv, K - 1);
                             ki = __shfl_sync(FULL, ti, K - 1);
                             // prune: drop the inserted lane and everything the new k-th key now rejects
-                            cand = cand && lane != src && key_before(sc, j, kv, ki);
-                            cm = __ballot_sync(FULL, cand);
+                            cnd = cnd && lane != src && key_before(sc, j, kv, ki);
+                            cm = __ballot_sync(FULL, cnd);
                         }
                     }
                 }
                 thr = (ki >= 0) ? __longlong_as_double(__double_as_longlong(kv) - 1) : fmax(kv, 0.0);
+                thr32 = float_floor(fmax(kv - K2_MARGIN, 0.0));
             }
             __syncwarp();
             // dense clear, 16 B per lane per store
             {
                 double2 *a2 = reinterpret_cast<double2 *>(acc);
                 const double2 z = make_double2(0.0, 0.0);
-                for (int q = lane; q < (T >> 1); q += 32) a2[q] = z;
+                for (int q = lane; q < (T * ES >> 4); q += 32) a2[q] = z;
             }
             __syncwarp();
         }
+        if (APPROX && ncand > 0) { __syncwarp(); score_round(ncand); __syncwarp(); }       // leftovers (ncand < 32)
         if (lane < K) {
             const size_t o = ((size_t)split * P.n_from + i) * K + lane;
             P.top_idx[o] = ti;
@@ -505,7 +688,7 @@ using namespace pfz;
 extern "C" {
 
 int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double *data, int32_t n_rows, int32_t n_vocab, int32_t tile,
-                    int32_t n_tiles, int32_t flags, int32_t *seg, uint16_t *post_idx, double *post_val, void *ws, void *stream) {
+                    int32_t n_tiles, int32_t flags, int32_t *seg, uint16_t *post_idx, double *post_val, float *post_val32, void *ws, void *stream) {
     PFZ_REQUIRE(tile > 0 && tile <= 65536, "pfz_index_build: tile %d out of range (1..65536)", tile);
     PFZ_REQUIRE((int64_t)n_tiles * tile >= n_rows, "pfz_index_build: n_tiles*tile < n_rows");
     const int64_t ncell = (int64_t)n_vocab * n_tiles;
@@ -529,19 +712,26 @@ int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double 
             index_bank_order_kernel<<<grid_for2(ncell, 128, 148 * 16), 128, 0, st>>>(seg, ncell, post_idx, post_val);
             PFZ_LAUNCH_OK();
         }
+        if (post_val32) {                                       // fp32 copy of the weights for the mixed-precision filter
+            to_f32_kernel<<<148 * 8, 256, 0, st>>>(post_val, 0, seg + ncell, post_val32);
+            PFZ_LAUNCH_OK();
+        }
     }
     return 0;
 }
 
 int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from, const int32_t *seg,
-                   const uint16_t *post_idx, const double *post_val, int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to, int32_t k,
+                   const uint16_t *post_idx, const double *post_val, const float *post_val32, const int32_t *b_indptr,
+                   const int32_t *b_indices, const double *b_data, int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to, int32_t k,
                    double min_similarity, int32_t self_match, int64_t from_index_base, int64_t to_index_base, int32_t n_splits,
                    const double *excl_val, const int32_t *excl_idx, int32_t *top_idx, double *top_val, int32_t *row_counter,
                    int32_t variant, void *stream) {
     PFZ_REQUIRE(k >= 1 && k <= 32, "pfz_spcos_topk: k=%d unsupported (1..32 per call; page with excl_* for more)", k);
     PFZ_REQUIRE(tile > 0 && tile <= 65536 && (tile % 64) == 0, "pfz_spcos_topk: tile %d must be a multiple of 64 in 64..65536", tile);
     PFZ_REQUIRE(n_splits >= 1 && n_splits <= n_tiles, "pfz_spcos_topk: n_splits %d out of range", n_splits);
-    PFZ_REQUIRE(variant == PFZ_K2_LIST || variant == PFZ_K2_DENSE, "pfz_spcos_topk: unknown variant %d", variant);
+    PFZ_REQUIRE(variant == PFZ_K2_LIST || variant == PFZ_K2_DENSE || variant == PFZ_K2_DENSE32, "pfz_spcos_topk: unknown variant %d", variant);
+    PFZ_REQUIRE(variant != PFZ_K2_DENSE32 || (post_val32 && b_indptr && b_indices && b_data),
+                "pfz_spcos_topk: PFZ_K2_DENSE32 needs post_val32 and the to-matrix CSR");
     if (n_from <= 0) return 0;
     cudaStream_t st = as_stream(stream);
     int dev = 0, sms = 0, smem_max = 0;
@@ -549,7 +739,8 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
     PFZ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     PFZ_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     PFZ_CUDA_OK(cudaMemsetAsync(row_counter, 0, sizeof(int32_t) * (size_t)n_splits, st));
-    SpcosParams P{a_indptr, a_indices, a_data, n_from, seg, post_idx, post_val, n_vocab, tile, n_tiles, n_to, k, min_similarity, self_match,
+    SpcosParams P{a_indptr, a_indices, a_data, n_from, seg, post_idx, post_val, post_val32, b_indptr, b_indices, b_data,
+                  n_vocab, tile, n_tiles, n_to, k, min_similarity, self_match,
                   from_index_base, to_index_base, n_splits, excl_val, excl_idx, top_idx, top_val, row_counter};
     auto launch = [&](auto kernel, int warps, size_t smem) -> int {
         PFZ_REQUIRE(smem <= (size_t)smem_max, "pfz_spcos_topk: tile %d needs %zu B shared memory > %d available", tile, smem, smem_max);
@@ -570,12 +761,16 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
         return launch(spcos_list_kernel<WARPS>, WARPS, (size_t)WARPS * tile * 10);
     }
     constexpr int WARPS = 2;
-    auto arena_of = [&](int D) { return (((size_t)(tile + 2) * 8 + (size_t)((tile >> 5) + 32 + 2 * D) * sizeof(WorkItem) + (size_t)tile + 16) + 15) & ~(size_t)15; };
+    const int es = variant == PFZ_K2_DENSE32 ? 4 : 8;
+    auto arena_of = [&](int D) { return (((size_t)(tile + 4) * es + (size_t)((tile >> 5) + 32 + 2 * D) * sizeof(WorkItem) + (size_t)tile + 16 + 256) + 15) & ~(size_t)15; };
     const char *env_d = getenv("PFZ_K2_DEPTH");                  // developer knob (pipeline depth); default 4
     const int depth = env_d ? atoi(env_d) : 4;
-    if (depth == 8) return launch(spcos_dense_kernel<WARPS, 8>, WARPS, (size_t)WARPS * arena_of(8));
-    if (depth == 2) return launch(spcos_dense_kernel<WARPS, 2>, WARPS, (size_t)WARPS * arena_of(2));
-    return launch(spcos_dense_kernel<WARPS, 4>, WARPS, (size_t)WARPS * arena_of(4));
+    if (variant == PFZ_K2_DENSE32) {
+        if (depth == 8) return launch(spcos_dense_kernel<WARPS, 8, true>, WARPS, (size_t)WARPS * arena_of(8));
+        return launch(spcos_dense_kernel<WARPS, 4, true>, WARPS, (size_t)WARPS * arena_of(4));
+    }
+    if (depth == 8) return launch(spcos_dense_kernel<WARPS, 8, false>, WARPS, (size_t)WARPS * arena_of(8));
+    return launch(spcos_dense_kernel<WARPS, 4, false>, WARPS, (size_t)WARPS * arena_of(4));
 }
 
 int pfz_topk_merge(const int32_t *idx, const double *val, int32_t n_lists, int32_t n_from, int32_t k_in, int32_t k_out, int32_t *out_idx,

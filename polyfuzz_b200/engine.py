@@ -112,7 +112,7 @@ class CsrMatrix:
 
 class StagedStrings:
     """One string list packed and resident in HBM (UTF-32 blob, offsets, n-gram slot prefix)."""
-    __slots__ = ("n", "n_chars", "d_blob", "d_off", "occ_ptr", "d_long", "n_long", "cap", "h2d_bytes", "lo", "hi")
+    __slots__ = ("n", "n_chars", "d_blob", "d_off", "occ_ptr", "d_long", "n_long", "cap", "h2d_bytes", "lo", "hi", "max_slots")
 
 
 def stage_strings(strings, lo, hi):
@@ -126,6 +126,7 @@ def stage_strings(strings, lo, hi):
     long_rows = np.nonzero(slots > WARP_ROW_SLOTS)[0].astype(np.int32)
     S = StagedStrings()
     S.n, S.n_chars, S.cap, S.lo, S.hi = len(strings), int(blob.size), int(occ[-1]), lo, hi
+    S.max_slots = int(slots.max()) if len(slots) else 0        # upper bound of any row's nnz
     S.d_blob = _to_dev(blob.view(np.int32), torch.int32) if blob.size else torch.zeros(1, dtype=torch.int32, device=_dev())
     S.d_off = _to_dev(offsets)
     S.occ_ptr = _to_dev(occ)
@@ -159,6 +160,7 @@ class NgramTfidf:
         self.idf = None                 # numpy float64[V]
         self.df = None
         self.n_fit_docs = 0
+        self.max_row_nnz = 0            # upper bound over every list seen (fit and transform)
         self._d_sym = self._d_vocab = self._d_idf = self._d_rank = None
 
     # ---- pickling: device tensors are rebuilt lazily ---------------------------------------------
@@ -194,6 +196,7 @@ class NgramTfidf:
 
     # ---- stage A ----------------------------------------------------------------------------------
     def _stage_a(self, S, d_sym):
+        self.max_row_nnz = max(self.max_row_nnz, S.max_slots)
         R = _Rows()
         R.n, R.cap, R.occ_ptr = S.n, S.cap, S.occ_ptr
         R.codes = torch.empty(max(R.cap, 1), dtype=torch.int64, device=_dev())
@@ -345,7 +348,8 @@ class NgramTfidf:
 
 # to-tile rows per K2 variant: the list kernel wants many small per-warp arenas (occupancy), the dense
 # kernel few large ones (long segments; it pipelines its own loads)
-DEFAULT_TILE = {"list": int(os.environ.get("PFZ_TILE_LIST", "512")), "dense": int(os.environ.get("PFZ_TILE_DENSE", "1024"))}
+DEFAULT_TILE = {"list": int(os.environ.get("PFZ_TILE_LIST", "512")), "dense": int(os.environ.get("PFZ_TILE_DENSE", "1024")),
+                "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1536"))}
 K2_WARPS = 8
 
 
@@ -368,16 +372,27 @@ class SparseIndex:
         cap = max(csr.indices.numel(), 1)
         self.post_idx = torch.empty(cap, dtype=torch.int16, device=dev)          # uint16 tile-local row
         self.post_val = torch.empty(cap, dtype=torch.float64, device=dev)
+        self.post_val32 = torch.empty(cap, dtype=torch.float32, device=dev) if variant == "dense32" else None
+        self.csr = csr                                          # the to-matrix itself (exact re-scoring in dense32)
         ws = _ws((ncell + 1) * 4 + 512 + _lib.load().pfz_scan_ws_bytes(ncell + 1))
         flags = 1 if os.environ.get("PFZ_BANK_ORDER", "1") != "0" else 0
         _lib.call("pfz_index_build", _p(csr.indptr), _p(csr.indices), _p(csr.data), n, self.n_vocab, tile,
-                  self.n_tiles, flags, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(ws), _stream())
+                  self.n_tiles, flags, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(self.post_val32), _p(ws), _stream())
 
 
-def choose_variant(density):
-    """dense when `density` = postings visited per scored pair (NgramTfidf.density()) is at least
-    DENSE_MIN_DENSITY, else list."""
-    return "dense" if (density is not None and density >= DENSE_MIN_DENSITY) else "list"
+DENSE32_MAX_ROW_NNZ = 128
+
+
+def choose_variant(density, max_row_nnz=None):
+    """K2 variant for an index: `list` for sparse inputs (density = postings visited per scored pair,
+    NgramTfidf.density(), below DENSE_MIN_DENSITY), else the dense-regime kernel.  The mixed-precision
+    `dense32` filter needs its fp32 error bound (<= ~row_nnz * 2^-24) to stay below half its 2e-5 margin,
+    so rows longer than DENSE32_MAX_ROW_NNZ n-grams select the plain fp64 `dense` kernel."""
+    if density is None or density < DENSE_MIN_DENSITY:
+        return "list"
+    if DENSE_VARIANT == "dense32" and (max_row_nnz is None or max_row_nnz > DENSE32_MAX_ROW_NNZ):
+        return "dense"
+    return DENSE_VARIANT
 
 
 def _auto_splits(n_from, n_tiles, sm_count=148):
@@ -387,9 +402,10 @@ def _auto_splits(n_from, n_tiles, sm_count=148):
     return max(1, min(n_tiles, (want + max(n_from, 1) - 1) // max(n_from, 1)))
 
 
-K2_LIST, K2_DENSE = 1, 2
+K2_LIST, K2_DENSE, K2_DENSE32 = 1, 2, 3
 DENSE_MIN_DENSITY = float(os.environ.get("PFZ_DENSE_MIN_DENSITY", "0.03"))
-K2_VARIANT = {"list": K2_LIST, "dense": K2_DENSE}
+DENSE_VARIANT = os.environ.get("PFZ_DENSE_VARIANT", "dense32")   # which kernel serves the dense regime
+K2_VARIANT = {"list": K2_LIST, "dense": K2_DENSE, "dense32": K2_DENSE32}
 
 
 def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_match=False, from_index_base=0,
@@ -415,8 +431,10 @@ def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_mat
         kp = min(32, remaining)
         ti = torch.empty((n_splits, max(n_from, 1), kp), dtype=torch.int32, device=dev)
         tv = torch.empty((n_splits, max(n_from, 1), kp), dtype=torch.float64, device=dev)
+        if variant == "dense32" and index.post_val32 is None:
+            raise ValueError("the index was not built for the dense32 variant")
         _lib.call("pfz_spcos_topk", _p(a.indptr), _p(a.indices), _p(a.data), n_from, _p(index.seg), _p(index.post_idx),
-                  _p(index.post_val), index.n_vocab, index.tile, index.n_tiles, index.n_to, kp, float(min_similarity),
+                  _p(index.post_val), _p(index.post_val32), _p(index.csr.indptr), _p(index.csr.indices), _p(index.csr.data), index.n_vocab, index.tile, index.n_tiles, index.n_to, kp, float(min_similarity),
                   int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, _p(excl_v), _p(excl_i),
                   _p(ti), _p(tv), _p(counter), K2_VARIANT[variant], _stream())
         if n_splits > 1:

@@ -93,11 +93,11 @@ class TFIDF(BaseMatcher):
             # fit / index on the whole list, score only the block's rows (global diagonal excluded)
             self._extract_tf_idf(from_list, None, re_train)
             block = self.vectorizer.transform(from_list[lo:hi])
-            idx, val = engine.spcos_topk(block, self._index, top_n, self.min_similarity, self_match=True,
+            idx, val = engine.spcos_topk(block, self._safe_index(), top_n, self.min_similarity, self_match=True,
                                          from_index_base=lo)
             return idx, val, top_n
         tf_idf_from, tf_idf_to = self._extract_tf_idf(from_list, to_list, re_train)
-        idx, val = engine.spcos_topk(tf_idf_from, self._index, top_n, self.min_similarity,
+        idx, val = engine.spcos_topk(tf_idf_from, self._safe_index(), top_n, self.min_similarity,
                                      self_match=to_list is None)
         return idx, val, top_n
 
@@ -124,7 +124,7 @@ class TFIDF(BaseMatcher):
                 self._index = None
             tf_idf_from = self._device_to()
         if self._index is None:
-            self._index = engine.SparseIndex(self._device_to(), variant=engine.choose_variant(vec.density()))
+            self._index = engine.SparseIndex(self._device_to(), variant=engine.choose_variant(vec.density(), vec.max_row_nnz))
         return tf_idf_from, self.tf_idf_to
 
     def _match_sharded(self, comm, from_list, to_list, re_train, top_n, from_block=None):
@@ -153,6 +153,13 @@ class TFIDF(BaseMatcher):
         if re_train:
             self.tf_idf_to, self._index = csr_to, index
         return idx, val
+
+    def _safe_index(self):
+        """A later transform() may bring from-rows longer than the mixed-precision bound allows: rebuild the
+        index for the fp64 kernel then (the to-matrix is unchanged)."""
+        if self._index.variant == "dense32" and self.vectorizer.max_row_nnz > engine.DENSE32_MAX_ROW_NNZ:
+            self._index = engine.SparseIndex(self._device_to(), variant="dense")
+        return self._index
 
     def _device_to(self):
         if hasattr(self.tf_idf_to, "tocsr"):                      # restored from a pickle

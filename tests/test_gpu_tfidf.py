@@ -106,7 +106,7 @@ def test_company_slice_vectoriser_bit_exact(pf, company):
     _csr_eq(v.emit(rows), g["csr_indptr"], g["csr_indices"], g["csr_data"], g["csr_shape"])
 
 
-@pytest.mark.parametrize("variant", ["list", "dense"])
+@pytest.mark.parametrize("variant", ["list", "dense", "dense32"])
 @pytest.mark.parametrize("tile", [None, 256, 1024])
 @pytest.mark.parametrize("n_splits", [1, 3])
 def test_company_slice_topk_vs_oracle_and_reference(pf, company, tile, n_splits, variant):
@@ -153,12 +153,18 @@ def _oracle_two(frm, to, rng=(3, 3), clean=True, rs=True):
     return f, t
 
 
-@pytest.mark.parametrize("variant", ["list", "dense"])
+def _force_variant(monkeypatch, engine, variant):
+    monkeypatch.setattr(engine, "DENSE_MIN_DENSITY", 1e9 if variant == "list" else 0.0)
+    monkeypatch.setattr(engine, "DENSE_VARIANT", variant if variant != "list" else "dense")
+    monkeypatch.setattr(engine, "DENSE32_MAX_ROW_NNZ", 1 << 30)        # exercise the filter even on long rows
+
+
+@pytest.mark.parametrize("variant", ["list", "dense", "dense32"])
 @pytest.mark.parametrize("k,ms", [(1, 0.0), (5, 0.3), (32, 0.0), (40, 0.0), (70, 0.05)])
 def test_synthetic_two_list_vs_oracle(pf, k, ms, variant, monkeypatch):
     polyfuzz_b200, engine = pf
     from polyfuzz_b200 import synth
-    monkeypatch.setattr(engine, "DENSE_MIN_DENSITY", 0.0 if variant == "dense" else 1e9)
+    _force_variant(monkeypatch, engine, variant)
     to = synth.company_names(6000, seed=3)
     frm = synth.company_names(2500, seed=4) + ["", "a", "ab", "  ", "!!!", to[17], to[17].lower()]
     m = polyfuzz_b200.TFIDF(min_similarity=ms, top_n=k)
@@ -236,13 +242,13 @@ def test_from_block_is_a_row_block_of_the_self_match(pf):
     assert blk.reset_index(drop=True).equals(full.iloc[1000:1800].reset_index(drop=True))
 
 
-@pytest.mark.parametrize("variant", ["list", "dense"])
+@pytest.mark.parametrize("variant", ["list", "dense", "dense32"])
 def test_every_row_shares_many_heavy_terms(pf, variant, monkeypatch):
     """All rows share ~20 trigrams, so every (term, tile) segment is the full tile: per-unit work far
     exceeds the dense kernel's work-item table (batched consumption) and every accumulator gets ~20
     additions in term order."""
     polyfuzz_b200, engine = pf
-    monkeypatch.setattr(engine, "DENSE_MIN_DENSITY", 0.0 if variant == "dense" else 1e9)
+    _force_variant(monkeypatch, engine, variant)
     names = [f"alpha beta gamma delta {i:05d} {'x' * (i % 7)}{i % 13}" for i in range(2600)]
     m = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=7)
     idx, val, k = m.match_arrays(names)
@@ -272,3 +278,24 @@ def test_shard_emulation_equals_unsharded(pf):
         parts_i.append(i_); parts_v.append(v_)
     mi, mv = engine.topk_merge(torch.stack(parts_i), torch.stack(parts_v), 10)
     assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
+
+
+def test_dense32_many_exact_ties_and_identical_rows(pf, monkeypatch):
+    """The fp32 filter must hand every row near the k-th key to the exact re-scoring: lists full of duplicates
+    (scores exactly 1.0 and large groups of exactly tied scores)."""
+    polyfuzz_b200, engine = pf
+    _force_variant(monkeypatch, engine, "dense32")
+    names = ["acme holdings inc"] * 40 + ["acme holding inc"] * 40 + [f"zeta {i % 5} llc" for i in range(300)] + ["unique name ltd"]
+    m = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=12)
+    idx, val, k = m.match_arrays(names)
+    a = m.tf_idf_to.to_scipy()
+    oi, ov = onative.spdot_topn(a, a, k, 0.0, self_match=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(val.cpu().numpy(), ov)
+
+
+def test_variant_selection_rules(pf):
+    _, engine = pf
+    assert engine.choose_variant(0.001, 20) == "list" and engine.choose_variant(None, 20) == "list"
+    assert engine.choose_variant(0.3, 69) == engine.DENSE_VARIANT
+    assert engine.choose_variant(0.3, 5000) == "dense" and engine.choose_variant(0.3, None) == "dense"

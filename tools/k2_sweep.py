@@ -31,7 +31,7 @@ ip = csr.indptr.cpu().numpy(); nnz = int(ip[-1])
 df = np.bincount(csr.indices[:nnz].cpu().numpy(), minlength=v.n_vocab).astype(np.float64)
 P = float((df * df).sum())
 print(f"n={n} V={v.n_vocab} nnz={nnz} P={P:.4g} fit(stageA+vocab incl. H2D, host idf)={t_fit:.2f} ms emit={t_emit:.2f} ms wall={time.time()-t0:.2f}s")
-variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["dense", "list"]
+variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["dense32", "dense", "list"]
 ref = None
 for variant in variants:
   for tile in tiles:
