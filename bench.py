@@ -301,7 +301,7 @@ def run_b200(args):
         except Exception:
             traffic = None
     achieved = b_alg / (k2_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "pfz::spcos_dense_kernel (K2)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "pfz::spcos_dense_kernel (K2, variant %s)" % result["index"].variant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_alg, "postings_per_launch": P, "kernel_ms_avg": k2_avg_ms,
                 "kernel_share_of_step": k2_avg_ms / ms_per_step,
@@ -327,7 +327,7 @@ def run_b200(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config_dict(n, world, {"tile": result["index"].tile, "V": vec.n_vocab, "nnz": nnz}),
+            "data": "synthetic", "config": config_dict(n, world, {"tile": result["index"].tile, "k2_variant": result["index"].variant, "V": vec.n_vocab, "nnz": nnz}),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "step_ms_each": [round(x, 3) for x in step_ms]}
     print(json.dumps(line), flush=True)

@@ -120,6 +120,7 @@ int64_t pfz_scan_ws_bytes(int64_t n);
 int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double *data, int32_t n_rows,
                     int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t flags,
                     int32_t *seg, uint16_t *post_idx, double *post_val, float *post_val32 /* may be NULL */,
+                    float *term_maxw /* float[n_vocab], max weight per term rounded up; may be NULL */,
                     void *ws, void *stream);
 
 /* top-k of (from CSR) x (to inverted index).
@@ -136,13 +137,16 @@ int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double 
  *                            sums decide which to-rows could rank before the k-th key (margin 2e-5); each of
  *                            those is re-scored exactly from the two CSR rows (b_* = the to-matrix CSR the index
  *                            was built from), so indices and scores are bit-identical to the other variants.
- *                            Requires l2-normalised rows with positive weights (TF-IDF).                      */
+ *                            Requires l2-normalised rows with positive weights (TF-IDF).  With term_maxw the
+ *                            kernel also skips whole posting lists whose summed upper bound cannot lift a
+ *                            to-row over the k-th key (MaxScore-style; exactness is kept by the re-scoring). */
 #define PFZ_K2_LIST  1
 #define PFZ_K2_DENSE 2
 #define PFZ_K2_DENSE32 3
 int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from,
                    const int32_t *seg, const uint16_t *post_idx, const double *post_val,
                    const float *post_val32, const int32_t *b_indptr, const int32_t *b_indices, const double *b_data,
+                   const float *term_maxw,
                    int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to,
                    int32_t k, double min_similarity, int32_t self_match,
                    int64_t from_index_base, int64_t to_index_base, int32_t n_splits,

@@ -34,7 +34,7 @@ __global__ void index_count_kernel(const int32_t *__restrict__ indptr, const int
 
 __global__ void index_fill_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, const double *__restrict__ data,
                                   int n_rows, int tile, int n_tiles, const int32_t *__restrict__ seg, int32_t *__restrict__ cur,
-                                  uint16_t *__restrict__ post_idx, double *__restrict__ post_val) {
+                                  uint16_t *__restrict__ post_idx, double *__restrict__ post_val, int *__restrict__ term_maxw_bits) {
     const int lane = lane_id();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (int r = gw; r < n_rows; r += nw) {
@@ -44,6 +44,8 @@ __global__ void index_fill_kernel(const int32_t *__restrict__ indptr, const int3
             const int pos = seg[c] + atomicAdd(&cur[c], 1);
             post_idx[pos] = (uint16_t)(r - tau * tile);
             post_val[pos] = data[p];
+            // per-term maximum weight, rounded up to fp32 (positive floats order like their bit patterns)
+            if (term_maxw_bits) atomicMax(&term_maxw_bits[indices[p]], __float_as_int(__double2float_ru(data[p])));
         }
     }
 }
@@ -109,6 +111,7 @@ struct SpcosParams {
     const int32_t *a_indptr; const int32_t *a_indices; const double *a_data; int n_from;
     const int32_t *seg; const uint16_t *post_idx; const double *post_val;
     const float *post_val32; const int32_t *b_indptr; const int32_t *b_indices; const double *b_data;   // mixed-precision variant
+    const float *term_maxw; float prune_alpha;      // upper-bound pruning (mixed-precision variant only; term_maxw may be NULL)
     int n_vocab, tile, n_tiles, n_to;
     int k; double min_sim; int self_match; int64_t from_base, to_base;
     int n_splits; const double *excl_val; const int32_t *excl_idx;
@@ -243,8 +246,6 @@ struct __align__(16) WorkItem { int off; int cnt; double v; };
 // Explicit 32-bit shared-window addresses and predicated instructions: the generic-pointer forms made
 // the compiler re-derive the shared window base and wrap every item in convergence barriers.
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
 // work item {int off; int cnt; double v} with one 16-byte load
 __device__ __forceinline__ void lds_item(unsigned a, unsigned &off, int &cnt, double &v) {
     unsigned lo, hi;
@@ -272,12 +273,6 @@ __device__ __forceinline__ void rmw_posting(unsigned acc_s, unsigned flags_s, un
                  "setp.gt.f64 q, o, %7; setp.gt.and.f64 r, n, %7, !q; mov.b16 one, 1;\n\t"
                  "@r st.shared.u8 [f], one; selp.u32 %0, 1, %0, r; }"
                  : "+r"(any) : "r"(acc_s), "r"(flags_s), "r"(row), "r"(dummy), "d"(v), "d"(w), "d"(thr) : "memory");
-}
-__device__ __forceinline__ void flag_if_crossed(unsigned flag_addr, double old, double nw, double thr, unsigned &any) {
-    asm volatile("{ .reg .pred p, q; .reg .b16 one; mov.b16 one, 1;\n\t"
-                 "setp.gt.f64 p, %1, %3; setp.gt.and.f64 q, %2, %3, !p;\n\t"
-                 "@q st.shared.u8 [%4], one; selp.u32 %0, 1, %0, q; }"
-                 : "+r"(any) : "d"(old), "d"(nw), "d"(thr), "r"(flag_addr) : "memory");
 }
 
 
@@ -331,7 +326,7 @@ __device__ __forceinline__ float float_floor(double x) {
     return f;
 }
 
-template <int WARPS, int D, bool APPROX>
+template <int WARPS, int D, bool APPROX, bool PRUNE>
 __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosParams P) {
     extern __shared__ __align__(16) unsigned char dyn[];
     const int lane = lane_id();
@@ -378,7 +373,7 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
         // not full (strict; untouched sums are 0) and the double just below kv once it is (inclusive: ties are
         // settled on the index at the end of the unit)
         double thr = fmax(P.min_sim, 0.0);
-        float thr32 = float_floor(fmax(P.min_sim - K2_MARGIN, 0.0));
+        float thr32 = float_floor(fmax(P.min_sim - K2_MARGIN, 0.0));     // flag threshold of the fp32 filter (see flag_thr)
         double xv = 0.0; int xi = -1; bool has_x = false;
         if (P.excl_val) { xv = P.excl_val[i]; xi = P.excl_idx[i]; has_x = xi >= 0; }
         const int64_t self_j = P.from_base + i - P.to_base;
@@ -389,7 +384,7 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
 
         // exact scoring + insertion of up to 32 candidates (one per lane); mixed precision batches its flagged rows
         // across units so that each round of dependent CSR loads serves a full warp
-        int ncand = 0;
+        int ncand = 0; bool need_reselect = false;
         auto score_round = [&](int n_round) {
             double sc = 0.0; int j = -1; bool cnd = false;
             if (lane < n_round) {
@@ -417,16 +412,51 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                 cnd = cnd && lane != src && key_before(sc, j, kv, ki);
                 cm = __ballot_sync(FULL, cnd);
             }
-            thr32 = float_floor(fmax(kv - K2_MARGIN, 0.0));
+            need_reselect = true;
         };
 
         // rows with <= 32 terms (the common case) keep their terms in registers across tiles
         int t_reg = 0; double v_reg = 0.0; int prev_end = 0;
         if (m <= 32 && lane < m) { t_reg = P.a_indices[a0 + lane]; v_reg = P.a_data[a0 + lane]; }
 
+        // Upper-bound pruning (mixed precision, rows of <= 32 terms).  Term t can add at most ub_t = v_t * max_j w_jt
+        // to any score.  A set NE of terms with sum ub < alpha * (kth - MARGIN) is skipped altogether (heavy, low-idf
+        // n-grams such as "inc": long posting lists, tiny contributions); the flag threshold drops by that sum, so
+        // every to-row that could still reach the k-th key is flagged by its remaining terms and scored exactly from
+        // the CSR rows (which include the skipped terms).  Re-selected whenever the k-th key has moved.
+        bool skip_term = false; float ub_ne = 0.f;
+        float ub_k = 0.f; int df_k = 0;
+        const bool prune = PRUNE && APPROX && P.term_maxw != nullptr && m <= 32 && P.prune_alpha > 0.f;
+        if (prune && lane < m) {
+            ub_k = __fmul_ru(__double2float_ru(v_reg), P.term_maxw[t_reg]);
+            df_k = seg[(int64_t)(t_reg + 1) * n_tiles] - seg[(int64_t)t_reg * n_tiles];
+        }
+        auto select_ne = [&]() {
+            skip_term = false; ub_ne = 0.f;
+            if (!prune) return;
+            float budget = P.prune_alpha * fmaxf((float)(kv - K2_MARGIN), 0.f);
+            if (ki < 0) budget = 0.f;                               // list not full: every touched row is a candidate
+            for (int r = 0; r < 8; ++r) {                           // up to 8 terms, longest posting list first
+                int best = (lane < m && !skip_term && ub_k <= budget && df_k > 0) ? df_k : -1;
+                int who = lane;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    const int ob = __shfl_xor_sync(FULL, best, d), ow = __shfl_xor_sync(FULL, who, d);
+                    if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; }
+                }
+                if (best < 0) break;
+                const float u = __shfl_sync(FULL, ub_k, who);
+                if (lane == who) skip_term = true;
+                ub_ne = __fadd_ru(ub_ne, u); budget -= u;
+            }
+        };
+        if (PRUNE) select_ne();
+        auto flag_thr = [&]() { return float_floor(fmax(fmax(kv - K2_MARGIN, 0.0) - (double)ub_ne, 0.0)); };
+
         for (int it = 0; it < ntau; ++it) {
             int tau = first_tau + it; if (tau >= tau_hi) tau -= ntau;
             bool any_post = false; unsigned crossed_any = 0u;
+            if (APPROX && need_reselect) { if (PRUNE) select_ne(); thr32 = flag_thr(); need_reselect = false; }
             for (int tb = 0; tb < m; tb += 32) {
                 const int kk = tb + lane;
                 int s = 0, len = 0; double v = 0.0;
@@ -437,7 +467,7 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                     const int e = seg[c + 1];
                     s = (m <= 32 && it > 0 && tau != tau_lo) ? prev_end : seg[c];
                     prev_end = e;
-                    len = e - s;
+                    len = (PRUNE && skip_term) ? 0 : e - s;
                 }
                 // work-item table: lane k appends its ceil(len/32) items at the exclusive prefix of the counts.
                 // A to-row may occur under several terms, so a term group can need more items than the table
@@ -548,7 +578,7 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                                 }
                             }
                         }
-                        gate = fmaxf(gate, float_floor(fmax((double)kth - K2_MARGIN, 0.0)));
+                        gate = fmaxf(gate, float_floor(fmax((double)kth - K2_MARGIN - (double)ub_ne, 0.0)));
                     }
                 }
                 for (int w0 = 0; w0 < T; w0 += 128) {               // 4 flag bytes per lane per step
@@ -612,7 +642,6 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                     }
                 }
                 thr = (ki >= 0) ? __longlong_as_double(__double_as_longlong(kv) - 1) : fmax(kv, 0.0);
-                thr32 = float_floor(fmax(kv - K2_MARGIN, 0.0));
             }
             __syncwarp();
             // dense clear, 16 B per lane per store
@@ -688,7 +717,8 @@ using namespace pfz;
 extern "C" {
 
 int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double *data, int32_t n_rows, int32_t n_vocab, int32_t tile,
-                    int32_t n_tiles, int32_t flags, int32_t *seg, uint16_t *post_idx, double *post_val, float *post_val32, void *ws, void *stream) {
+                    int32_t n_tiles, int32_t flags, int32_t *seg, uint16_t *post_idx, double *post_val, float *post_val32, float *term_maxw,
+                    void *ws, void *stream) {
     PFZ_REQUIRE(tile > 0 && tile <= 65536, "pfz_index_build: tile %d out of range (1..65536)", tile);
     PFZ_REQUIRE((int64_t)n_tiles * tile >= n_rows, "pfz_index_build: n_tiles*tile < n_rows");
     const int64_t ncell = (int64_t)n_vocab * n_tiles;
@@ -705,8 +735,9 @@ int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double 
     if (scan_exclusive_i32(seg, seg, ncell + 1, sws, st)) return 1;
     if (n_rows > 0) {
         PFZ_CUDA_OK(cudaMemsetAsync(cur, 0, ((size_t)ncell + 1) * 4, st));
+        if (term_maxw) PFZ_CUDA_OK(cudaMemsetAsync(term_maxw, 0, (size_t)n_vocab * 4, st));
         index_fill_kernel<<<grid_for2((int64_t)n_rows * 32, 256, 148 * 16), 256, 0, st>>>(indptr, indices, data, n_rows, tile, n_tiles, seg, cur,
-                                                                                            post_idx, post_val);
+                                                                                            post_idx, post_val, reinterpret_cast<int *>(term_maxw));
         PFZ_LAUNCH_OK();
         if (flags & PFZ_INDEX_BANK_ORDER) {
             index_bank_order_kernel<<<grid_for2(ncell, 128, 148 * 16), 128, 0, st>>>(seg, ncell, post_idx, post_val);
@@ -722,7 +753,7 @@ int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double 
 
 int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from, const int32_t *seg,
                    const uint16_t *post_idx, const double *post_val, const float *post_val32, const int32_t *b_indptr,
-                   const int32_t *b_indices, const double *b_data, int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to, int32_t k,
+                   const int32_t *b_indices, const double *b_data, const float *term_maxw, int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to, int32_t k,
                    double min_similarity, int32_t self_match, int64_t from_index_base, int64_t to_index_base, int32_t n_splits,
                    const double *excl_val, const int32_t *excl_idx, int32_t *top_idx, double *top_val, int32_t *row_counter,
                    int32_t variant, void *stream) {
@@ -739,7 +770,9 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
     PFZ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     PFZ_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     PFZ_CUDA_OK(cudaMemsetAsync(row_counter, 0, sizeof(int32_t) * (size_t)n_splits, st));
-    SpcosParams P{a_indptr, a_indices, a_data, n_from, seg, post_idx, post_val, post_val32, b_indptr, b_indices, b_data,
+    const char *env_a = getenv("PFZ_K2_PRUNE_ALPHA");            // developer knob; 0 disables upper-bound pruning
+    const float prune_alpha = env_a ? (float)atof(env_a) : 0.0f; // measured slower on the benchmark data: off by default
+    SpcosParams P{a_indptr, a_indices, a_data, n_from, seg, post_idx, post_val, post_val32, b_indptr, b_indices, b_data, term_maxw, prune_alpha,
                   n_vocab, tile, n_tiles, n_to, k, min_similarity, self_match,
                   from_index_base, to_index_base, n_splits, excl_val, excl_idx, top_idx, top_val, row_counter};
     auto launch = [&](auto kernel, int warps, size_t smem) -> int {
@@ -766,11 +799,12 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
     const char *env_d = getenv("PFZ_K2_DEPTH");                  // developer knob (pipeline depth); default 4
     const int depth = env_d ? atoi(env_d) : 4;
     if (variant == PFZ_K2_DENSE32) {
-        if (depth == 8) return launch(spcos_dense_kernel<WARPS, 8, true>, WARPS, (size_t)WARPS * arena_of(8));
-        return launch(spcos_dense_kernel<WARPS, 4, true>, WARPS, (size_t)WARPS * arena_of(4));
+        if (prune_alpha > 0.f && term_maxw) return launch(spcos_dense_kernel<WARPS, 4, true, true>, WARPS, (size_t)WARPS * arena_of(4));
+        if (depth == 8) return launch(spcos_dense_kernel<WARPS, 8, true, false>, WARPS, (size_t)WARPS * arena_of(8));
+        return launch(spcos_dense_kernel<WARPS, 4, true, false>, WARPS, (size_t)WARPS * arena_of(4));
     }
-    if (depth == 8) return launch(spcos_dense_kernel<WARPS, 8, false>, WARPS, (size_t)WARPS * arena_of(8));
-    return launch(spcos_dense_kernel<WARPS, 4, false>, WARPS, (size_t)WARPS * arena_of(4));
+    if (depth == 8) return launch(spcos_dense_kernel<WARPS, 8, false, false>, WARPS, (size_t)WARPS * arena_of(8));
+    return launch(spcos_dense_kernel<WARPS, 4, false, false>, WARPS, (size_t)WARPS * arena_of(4));
 }
 
 int pfz_topk_merge(const int32_t *idx, const double *val, int32_t n_lists, int32_t n_from, int32_t k_in, int32_t k_out, int32_t *out_idx,

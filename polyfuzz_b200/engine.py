@@ -373,11 +373,12 @@ class SparseIndex:
         self.post_idx = torch.empty(cap, dtype=torch.int16, device=dev)          # uint16 tile-local row
         self.post_val = torch.empty(cap, dtype=torch.float64, device=dev)
         self.post_val32 = torch.empty(cap, dtype=torch.float32, device=dev) if variant == "dense32" else None
+        self.term_maxw = torch.empty(max(self.n_vocab, 1), dtype=torch.float32, device=dev) if variant == "dense32" else None
         self.csr = csr                                          # the to-matrix itself (exact re-scoring in dense32)
         ws = _ws((ncell + 1) * 4 + 512 + _lib.load().pfz_scan_ws_bytes(ncell + 1))
         flags = 1 if os.environ.get("PFZ_BANK_ORDER", "1") != "0" else 0
         _lib.call("pfz_index_build", _p(csr.indptr), _p(csr.indices), _p(csr.data), n, self.n_vocab, tile,
-                  self.n_tiles, flags, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(self.post_val32), _p(ws), _stream())
+                  self.n_tiles, flags, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(self.post_val32), _p(self.term_maxw), _p(ws), _stream())
 
 
 DENSE32_MAX_ROW_NNZ = 128
@@ -434,7 +435,8 @@ def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_mat
         if variant == "dense32" and index.post_val32 is None:
             raise ValueError("the index was not built for the dense32 variant")
         _lib.call("pfz_spcos_topk", _p(a.indptr), _p(a.indices), _p(a.data), n_from, _p(index.seg), _p(index.post_idx),
-                  _p(index.post_val), _p(index.post_val32), _p(index.csr.indptr), _p(index.csr.indices), _p(index.csr.data), index.n_vocab, index.tile, index.n_tiles, index.n_to, kp, float(min_similarity),
+                  _p(index.post_val), _p(index.post_val32), _p(index.csr.indptr), _p(index.csr.indices), _p(index.csr.data),
+                  _p(index.term_maxw), index.n_vocab, index.tile, index.n_tiles, index.n_to, kp, float(min_similarity),
                   int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, _p(excl_v), _p(excl_i),
                   _p(ti), _p(tv), _p(counter), K2_VARIANT[variant], _stream())
         if n_splits > 1:
