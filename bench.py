@@ -220,9 +220,11 @@ def run_b200(args):
                                                      timings=k2_events if record_k2 else None)
         result["idx"], result["val"], result["vec"], result["csr"], result["index"] = idx, val, vec, csr_to, index
 
+    import gc
     for _ in range(args.warmup):
         flush.zero_(); device_step(False)
     barrier()
+    gc.collect(); gc.disable()                               # no collector pauses inside the timed steps
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.launch_count()
     step_ms = []
@@ -263,6 +265,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
     e2e_ms_per_step = float(e2e_total.item()) / len(e2e_ms)
+    gc.enable()
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
