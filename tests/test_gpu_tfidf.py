@@ -299,3 +299,45 @@ def test_variant_selection_rules(pf):
     assert engine.choose_variant(0.001, 20) == "list" and engine.choose_variant(None, 20) == "list"
     assert engine.choose_variant(0.3, 69) == engine.DENSE_VARIANT
     assert engine.choose_variant(0.3, 5000) == "dense" and engine.choose_variant(0.3, None) == "dense"
+
+
+@pytest.mark.parametrize("rng,clean", [((3, 6), True), ((2, 5), True), ((1, 3), False), ((3, 4), False)])
+def test_large_code_space_and_raw_mode_at_scale(pf, rng, clean):
+    """n-gram ranges whose code space exceeds the direct-addressed table (gather + bitonic sort + RLE vocabulary)
+    and the raw (clean_string=False) alphabet path, on a few thousand strings with non-ASCII letters."""
+    polyfuzz_b200, engine = pf
+    from polyfuzz_b200 import synth
+    to = synth.titles(2500, seed=31); frm = synth.titles(700, seed=32) + ["", "x", "Ünïcødé Çafé", to[3]]
+    m = polyfuzz_b200.TFIDF(n_gram_range=rng, clean_string=clean, min_similarity=0.0, top_n=5)
+    idx, val, k = m.match_arrays(frm, to)
+    f, t = _oracle_two(frm, to, rng, clean, True)
+    got_to = m.tf_idf_to.to_scipy()
+    assert got_to.shape == t.shape
+    np.testing.assert_array_equal(got_to.indptr, t.indptr)
+    np.testing.assert_array_equal(got_to.indices, t.indices)
+    np.testing.assert_array_equal(got_to.data, t.data)
+    oi, ov = onative.spdot_topn(f, t, k, 0.0, n_threads=8)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(val.cpu().numpy(), ov)
+
+
+def test_transform_after_pickle_with_unseen_and_empty_rows(pf, tmp_path):
+    import joblib
+    polyfuzz_b200, engine = pf
+    from polyfuzz_b200 import synth
+    to = synth.company_names(3000, seed=41); frm = synth.company_names(500, seed=42)
+    m = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=3)
+    m.match(frm, to)
+    new = synth.company_names(300, seed=43) + ["", "zzzzqqqq xxxyyy", "A"]
+    exp = m.match(new, to, re_train=False)
+    # oracle: fixed vocabulary / idf from the fit, unseen n-grams dropped
+    o = otfidf.TfidfOracle().fit(list(to) + list(frm))
+    oi, ov = onative.spdot_topn(o.transform(new), o.transform(to), 3, 0.0)
+    ref = oracle_assemble(new, to, oi, ov)
+    for c in exp.columns:
+        g = [None if (isinstance(v, float) and np.isnan(v)) else v for v in exp[c].tolist()]
+        e = [None if (isinstance(v, float) and np.isnan(v)) else v for v in ref[c].tolist()]
+        assert g == e, c
+    joblib.dump(m, tmp_path / "m.joblib")
+    got = joblib.load(tmp_path / "m.joblib").match(new, to, re_train=False)
+    assert got.equals(exp)
