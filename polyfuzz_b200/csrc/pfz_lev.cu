@@ -128,8 +128,10 @@ __global__ void __launch_bounds__(WARPS * 32) lev_kernel(const LevParams P) {
 #pragma unroll
                 for (int b = 0; b < NW; ++b) { Pv[b] = ~(W)0; Mv[b] = 0; }
                 int score = m;
+                uint32_t nextw = nmax > 0 ? src[0] : 0u;
                 for (int j0 = 0; j0 < nmax; j0 += 4) {
-                    const uint32_t word = src[(size_t)(j0 >> 2) * 32];
+                    const uint32_t word = nextw;
+                    if (j0 + 4 < nmax) nextw = src[(size_t)((j0 >> 2) + 1) * 32];      // prefetch: the recurrence below is a long dependent chain
 #pragma unroll
                     for (int bb = 0; bb < 4; ++bb) {
                         if (j0 + bb < n) {
@@ -163,8 +165,10 @@ __global__ void __launch_bounds__(WARPS * 32) lev_kernel(const LevParams P) {
                 W S[NW];
 #pragma unroll
                 for (int b = 0; b < NW; ++b) S[b] = ~(W)0;
+                uint32_t nextw = nmax > 0 ? src[0] : 0u;
                 for (int j0 = 0; j0 < nmax; j0 += 4) {
-                    const uint32_t word = src[(size_t)(j0 >> 2) * 32];
+                    const uint32_t word = nextw;
+                    if (j0 + 4 < nmax) nextw = src[(size_t)((j0 >> 2) + 1) * 32];
 #pragma unroll
                     for (int bb = 0; bb < 4; ++bb) {
                         if (j0 + bb < n) {

@@ -84,8 +84,9 @@ def edit_argbest(from_list, to_list, metric="ratio", score_cutoff=0.0, exclude_s
     slen = torch.empty(n_to, dtype=torch.int32, device=dev)
 
     if n_splits is None:
-        want = 148 * 8
-        n_splits = 1 if n_from >= want else max(1, min(n_grp, (want + n_from - 1) // n_from))
+        # ~4 (pattern, to-split) tasks per resident warp: patterns differ in length, finer tasks balance the tail
+        want = 4 * 148 * 48
+        n_splits = max(1, min(n_grp, (want + n_from - 1) // n_from))
     n_splits = max(1, min(int(n_splits), n_grp))
     part_idx = torch.full((n_splits, n_from), -1, dtype=torch.int32, device=dev)
     part_score = torch.zeros((n_splits, n_from), dtype=torch.float64, device=dev)

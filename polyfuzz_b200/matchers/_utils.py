@@ -21,7 +21,8 @@ _POOL = None
 def _pool():
     global _POOL
     if _POOL is None:
-        _POOL = ThreadPoolExecutor(max_workers=8, thread_name_prefix="pfz-assemble")
+        import os
+        _POOL = ThreadPoolExecutor(max_workers=max(4, min(32, (os.cpu_count() or 8) // 2)), thread_name_prefix="pfz-assemble")
     return _POOL
 
 
