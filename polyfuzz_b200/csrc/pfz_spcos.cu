@@ -304,7 +304,7 @@ __device__ __forceinline__ void rmw_posting32(unsigned acc_s, unsigned flags_s, 
                  "fma.rn.f32 n, %5, %6, o;\n\t"
                  "@p st.shared.f32 [a], n;\n\t"
                  "setp.gt.f32 q, o, %7; setp.gt.and.f32 r, n, %7, !q; mov.b16 one, 1;\n\t"
-                 "@r st.shared.u8 [f], one; selp.u32 %0, 1, %0, r; }"
+                 "@r st.shared.u8 [f], one; @r add.u32 %0, %0, 1; }"
                  : "+r"(any) : "r"(acc_s), "r"(flags_s), "r"(row), "r"(dummy), "f"(v), "f"(w), "f"(thr) : "memory");
 }
 // canonical score of (from-row a, to-row b): common terms in ascending order, product rounded, then added
@@ -546,12 +546,7 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                 // if its fp32 sum is within MARGIN of that value, so pass B re-scores just those.
                 float gate = thr32;
                 if (APPROX) {
-                    int nflag = 0;
-                    for (int w0 = 0; w0 < T; w0 += 128) {
-                        const int q4 = w0 + lane * 4;
-                        if (q4 < T) { const unsigned bits = *reinterpret_cast<const unsigned *>(flags + q4); nflag += __popc(bits & 0x01010101u); }
-                    }
-                    nflag = __reduce_add_sync(FULL, nflag);
+                    const int nflag = (int)__reduce_add_sync(FULL, crossed_any);   // each lane counted its own flags (rmw_posting32)
                     if (nflag > 2 * K + 32 && !has_x) {              // (paging excludes rows by exact key: no pre-selection then)
                         const float *acc32 = reinterpret_cast<const float *>(acc);
                         float lv = -1.f;                                  // lane r: r-th largest fp32 sum so far (r < K)
