@@ -326,8 +326,10 @@ __device__ __forceinline__ float float_floor(double x) {
     return f;
 }
 
+// Register caps measured on B200 (100k x 100k): the mixed-precision kernel is fastest at 64 registers (16 blocks of
+// 2 warps per SM, a few spilled bytes), the fp64 kernel at 80 (12 blocks); fewer registers spill into the hot loop.
 template <int WARPS, int D, bool APPROX, bool PRUNE>
-__global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosParams P) {
+__global__ void __launch_bounds__(WARPS * 32, (APPROX && !PRUNE && D <= 4) ? 16 : 12) spcos_dense_kernel(const SpcosParams P) {
     extern __shared__ __align__(16) unsigned char dyn[];
     const int lane = lane_id();
     const int w = threadIdx.x >> 5;
@@ -576,10 +578,18 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                         gate = fmaxf(gate, float_floor(fmax((double)kth - K2_MARGIN - (double)ub_ne, 0.0)));
                     }
                 }
-                for (int w0 = 0; w0 < T; w0 += 128) {               // 4 flag bytes per lane per step
-                    unsigned bits = 0u;
-                    const int q4 = w0 + lane * 4;
-                    if (q4 < T) { bits = *reinterpret_cast<const unsigned *>(flags + q4); if (bits) *reinterpret_cast<unsigned *>(flags + q4) = 0u; }
+                for (int w00 = 0; w00 < T; w00 += 512) {            // 16 flag bytes per lane per step; empty 512-row spans cost one vote
+                  uint4 fb = make_uint4(0u, 0u, 0u, 0u);
+                  const int q16 = w00 + lane * 16;
+                  if (q16 < T) {
+                      fb = *reinterpret_cast<const uint4 *>(flags + q16);
+                      if (fb.x | fb.y | fb.z | fb.w) *reinterpret_cast<uint4 *>(flags + q16) = make_uint4(0u, 0u, 0u, 0u);
+                  }
+                  if (!__any_sync(FULL, (fb.x | fb.y | fb.z | fb.w) != 0u)) continue;
+#pragma unroll
+                  for (int wsel = 0; wsel < 4; ++wsel) {
+                    unsigned bits = wsel == 0 ? fb.x : wsel == 1 ? fb.y : wsel == 2 ? fb.z : fb.w;
+                    const int q4 = q16 + wsel * 4;
                     while (__ballot_sync(FULL, bits != 0u)) {
                         if (APPROX) {
                             bool take = false; int jloc = 0;
@@ -635,6 +645,7 @@ __global__ void __launch_bounds__(WARPS * 32) spcos_dense_kernel(const SpcosPara
                             cm = __ballot_sync(FULL, cnd);
                         }
                     }
+                  }
                 }
                 thr = (ki >= 0) ? __longlong_as_double(__double_as_longlong(kv) - 1) : fmax(kv, 0.0);
             }

@@ -349,7 +349,7 @@ class NgramTfidf:
 # to-tile rows per K2 variant: the list kernel wants many small per-warp arenas (occupancy), the dense
 # kernel few large ones (long segments; it pipelines its own loads)
 DEFAULT_TILE = {"list": int(os.environ.get("PFZ_TILE_LIST", "512")), "dense": int(os.environ.get("PFZ_TILE_DENSE", "1024")),
-                "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1536"))}
+                "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1024"))}
 K2_WARPS = 8
 
 
