@@ -350,7 +350,6 @@ class NgramTfidf:
 # kernel few large ones (long segments; it pipelines its own loads)
 DEFAULT_TILE = {"list": int(os.environ.get("PFZ_TILE_LIST", "512")), "dense": int(os.environ.get("PFZ_TILE_DENSE", "1024")),
                 "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1024"))}
-K2_WARPS = 8
 
 
 class SparseIndex:
@@ -397,7 +396,7 @@ def choose_variant(density, max_row_nnz=None):
 
 
 def _auto_splits(n_from, n_tiles, sm_count=148):
-    want = sm_count * K2_WARPS * 2
+    want = sm_count * 32                                   # enough (from-row, tile-range) tasks to fill every SM
     if n_from >= want:
         return 1
     return max(1, min(n_tiles, (want + max(n_from, 1) - 1) // max(n_from, 1)))

@@ -68,7 +68,15 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.pfz_scan_ws_bytes(10) >= 256
-    assert _lib.launch_count() == 0 or _lib.launch_count() > 0
+    assert _lib.launch_count() >= 0
+    # every prototype of the header has the same number of parameters as its ctypes binding
+    hc = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|const char \*)\s*\*?\s*(pfz_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hc, flags=re.S)
+    assert {n for n, _ in protos} == declared
+    for name, args in protos:
+        args = args.strip()
+        n_args = 0 if args in ("void", "") else len(args.split(","))
+        assert n_args == len(_lib._PROTOS[name]), (name, n_args, len(_lib._PROTOS[name]))
 
 
 def test_plugin_contract():
