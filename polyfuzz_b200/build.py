@@ -37,7 +37,30 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+HOSTPACK_SRC = os.path.join(CSRC, "pfz_hostpack.c")
+
+
+def hostpack_path():
+    import sysconfig
+    return os.path.join(HERE, "_pfz_hostpack" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_hostpack(force=False):
+    """The small CPython extension that packs list[str] into blob + offsets (host marshalling, plain gcc)."""
+    import sysconfig
+    out = hostpack_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(HOSTPACK_SRC):
+        return out
+    env = dict(os.environ); env.pop("CC", None)
+    cmd = ["gcc", "-O3", "-fPIC", "-shared", "-I", sysconfig.get_paths()["include"], "-o", out, HOSTPACK_SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("gcc failed for pfz_hostpack.c:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force=False, verbose=False):
+    build_hostpack(force)
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + sources()

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from .engine import _dev, _p, _stream, _to_dev
-from .strings import pack_utf32
+from .strings import pack_strings
 
 METRIC = {"lev": 0, "indel": 1, "norm_lev": 2, "ratio": 3}
 N_CODE_POINTS = 0x110000
@@ -54,8 +54,8 @@ def edit_argbest(from_list, to_list, metric="ratio", score_cutoff=0.0, exclude_s
     [, matrix int32[n_from, n_to]]) as device tensors."""
     dev = _dev()
     n_from, n_to = len(from_list), len(to_list)
-    fblob, foff = pack_utf32(from_list)
-    tblob, toff = pack_utf32(to_list)
+    fblob, foff, _ = pack_strings(from_list)              # uint8 (ASCII list) or uint32 code points
+    tblob, toff, _ = pack_strings(to_list)
     flens = np.diff(foff)
     if n_from and flens.max() > MAX_LEN:
         raise ValueError(f"from-string {int(flens.argmax())} has {int(flens.max())} code points; the edit-distance "
@@ -68,9 +68,13 @@ def edit_argbest(from_list, to_list, metric="ratio", score_cutoff=0.0, exclude_s
         out = (best_idx[:n_from], best_score[:n_from], best_dist[:n_from])
         return out + (matrix[:n_from, :n_to],) if want_matrix else out
 
-    d_fblob = _to_dev(fblob.view(np.int32), torch.int32) if fblob.size else torch.zeros(1, dtype=torch.int32, device=dev)
+    def blob_to_dev(b):
+        if b.size == 0:
+            return torch.zeros(1, dtype=torch.int32, device=dev)
+        return _to_dev(b).to(torch.int32) if b.dtype == np.uint8 else _to_dev(b.view(np.int32), torch.int32)
+    d_fblob = blob_to_dev(fblob)
     d_foff = _to_dev(foff)
-    d_tblob = _to_dev(tblob.view(np.int32), torch.int32) if tblob.size else torch.zeros(1, dtype=torch.int32, device=dev)
+    d_tblob = blob_to_dev(tblob)
     d_toff = _to_dev(toff)
     # to-strings sorted by length, groups of 32, 4 symbols per word
     tlens = np.diff(toff)
@@ -99,6 +103,7 @@ def edit_argbest(from_list, to_list, metric="ratio", score_cutoff=0.0, exclude_s
     for lo, hi in _alphabet_batches(fblob, foff):
         cps = np.unique(fblob[foff[lo]:foff[hi]])
         table = np.zeros(N_CODE_POINTS, dtype=np.uint8)
+        cps = cps.astype(np.int64)
         table[cps[cps < N_CODE_POINTS]] = np.arange(1, len(cps) + 1, dtype=np.uint8)[:int((cps < N_CODE_POINTS).sum())]
         d_table = _to_dev(table)
         _lib.call("pfz_lev_pack", _p(d_tblob), _p(d_toff), _p(d_order), n_to, _p(d_table), _p(d_goff), _p(packed), _p(slen), _stream())

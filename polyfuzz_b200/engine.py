@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .strings import pack_utf32, ngram_slot_bounds
+from .strings import pack_utf32, pack_strings, ngram_slot_bounds
 
 FLAG_CLEAN, FLAG_REMOVE_SPACE = 1, 2
 WARP_ROW_SLOTS, MAX_ROW_SLOTS = 256, 8192
@@ -117,7 +117,7 @@ class StagedStrings:
 
 def stage_strings(strings, lo, hi):
     """Host marshalling + H2D of one list (the only per-string Python work on the path)."""
-    blob, offsets = pack_utf32(strings)
+    blob, offsets, _arrow = pack_strings(strings)
     slots, occ = ngram_slot_bounds(offsets, lo, hi)
     if len(slots) and slots.max() > MAX_ROW_SLOTS:
         r = int(slots.argmax())
@@ -127,7 +127,12 @@ def stage_strings(strings, lo, hi):
     S = StagedStrings()
     S.n, S.n_chars, S.cap, S.lo, S.hi = len(strings), int(blob.size), int(occ[-1]), lo, hi
     S.max_slots = int(slots.max()) if len(slots) else 0        # upper bound of any row's nnz
-    S.d_blob = _to_dev(blob.view(np.int32), torch.int32) if blob.size else torch.zeros(1, dtype=torch.int32, device=_dev())
+    if blob.size == 0:
+        S.d_blob = torch.zeros(1, dtype=torch.int32, device=_dev())
+    elif blob.dtype == np.uint8:                              # ASCII list: 1 byte per code point over PCIe, widened in HBM
+        S.d_blob = _to_dev(blob).to(torch.int32)
+    else:
+        S.d_blob = _to_dev(blob.view(np.int32), torch.int32)
     S.d_off = _to_dev(offsets)
     S.occ_ptr = _to_dev(occ)
     S.n_long = len(long_rows)

@@ -9,6 +9,7 @@ from ._base import BaseMatcher
 from ._utils import assemble_matches, clip_top_n, prepare_strings
 from .. import engine
 from ..distributed import get_comm, shard_bounds, tfidf_topk_sharded
+from ..strings import ARROW_CACHE
 
 
 class TFIDF(BaseMatcher):
@@ -69,11 +70,14 @@ class TFIDF(BaseMatcher):
         from_block=(lo, hi) (new, self-match only): return the matches of from_list[lo:hi] against the
         whole from_list (diagonal excluded) -- one row-block of a self-match that is too large for one
         call / one GPU; the frame has hi-lo rows."""
+        ARROW_CACHE.clear()
         top_idx, top_val, top_n = self.match_arrays(from_list, to_list, re_train, from_block)     # kernels are in flight
         rows = from_list if from_block is None else from_list[from_block[0]:from_block[1]]
         targets = to_list if to_list is not None else from_list
         prepared = prepare_strings(rows, targets if (to_list is not None or from_block is not None) else None)   # overlaps the GPU
-        return assemble_matches(rows, targets, top_idx.cpu().numpy(), top_val.cpu().numpy(), prepared=prepared)
+        out = assemble_matches(rows, targets, top_idx.cpu().numpy(), top_val.cpu().numpy(), prepared=prepared)
+        ARROW_CACHE.clear()
+        return out
 
     def match_arrays(self, from_list, to_list=None, re_train=True, from_block=None):
         """Device-side result: (top_idx int32[n,k] with -1 for no match, top_val float64[n,k], k)."""

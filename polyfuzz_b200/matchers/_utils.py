@@ -49,9 +49,16 @@ def prepare_strings(from_list, to_list):
     dt = _str_dtype()
     if dt is None or len(from_list) == 0:
         return None
+    from ..strings import ARROW_CACHE
+
+    def arrow_of(lst):
+        hit = ARROW_CACHE.get(id(lst))
+        if hit is not None and hit[0] is lst:               # packed (and converted) moments ago by the vectoriser
+            return hit[1]
+        return pa.array(lst, type=pa.large_string())
     same = to_list is None or to_list is from_list
-    to_pa = pa.array(from_list if same else to_list, type=pa.large_string())
-    from_pa = to_pa if same else pa.array(from_list, type=pa.large_string())
+    to_pa = arrow_of(from_list if same else to_list)
+    from_pa = to_pa if same else arrow_of(from_list)
     return from_pa, to_pa
 
 

@@ -30,3 +30,68 @@ def ngram_slot_bounds(offsets, lo, hi):
     occ = np.zeros(len(lens) + 1, dtype=np.int64)
     np.cumsum(slots, out=occ[1:])
     return slots, occ
+
+
+try:
+    import pyarrow as _pa
+    import pyarrow.compute as _pc
+except Exception:                                        # pragma: no cover
+    _pa = _pc = None
+
+# id(list) -> (list, Arrow array) of the lists packed by the current call; lets the frame assembly reuse them
+ARROW_CACHE = {}
+
+
+def _hostpack():
+    """The C packer (polyfuzz_b200/csrc/pfz_hostpack.c), or None if it has not been built."""
+    global _HP
+    if _HP is False:
+        try:
+            from . import _pfz_hostpack as hp
+            _HP = hp
+        except Exception:
+            _HP = None
+    return _HP
+
+
+_HP = False
+
+
+def pack_strings(strings):
+    """(blob, offsets, arrow_or_None): `blob` is uint8 (pure-ASCII list: bytes == code points, a zero-copy view of
+    the Arrow data buffer, widened to uint32 on the device) or uint32 (UTF-32).  The Arrow array is built once and
+    cached for the frame assembly; anything Arrow cannot take (lone surrogates, non-str) falls back to pack_utf32."""
+    n = len(strings)
+    hp = _hostpack()
+    if hp is not None and n and isinstance(strings, (list, tuple)):
+        total, ascii_only = hp.scan(strings)                  # one C pass; TypeError on non-str
+        blob = np.empty(max(total, 1), dtype=np.uint8 if ascii_only else np.uint32)
+        offsets = np.empty(n + 1, dtype=np.int64)
+        hp.fill(strings, blob, offsets, 1 if ascii_only else 4)
+        return blob[:total], offsets, None
+    if _pa is None or n == 0:
+        b, o = pack_utf32(strings)
+        return b, o, None
+    try:
+        arr = _pa.array(strings, type=_pa.large_string())
+        if arr.null_count:
+            raise TypeError("all elements of the string list must be str")
+        lens = _pc.utf8_length(arr).to_numpy(zero_copy_only=False).astype(np.int64, copy=False)
+    except TypeError:
+        raise
+    except Exception:
+        b, o = pack_utf32(strings)
+        return b, o, None
+    ARROW_CACHE[id(strings)] = (strings, arr)
+    bufs = arr.buffers()
+    byte_off = np.frombuffer(bufs[1], dtype=np.int64, count=n + 1, offset=arr.offset * 8)
+    total_bytes = int(byte_off[-1] - byte_off[0])
+    total_cp = int(lens.sum())
+    if total_bytes == total_cp:                           # pure ASCII
+        data = np.frombuffer(bufs[2], dtype=np.uint8, count=total_bytes, offset=int(byte_off[0])) if total_bytes else np.zeros(0, np.uint8)
+        offsets = byte_off - byte_off[0] if byte_off[0] else byte_off
+        return data, np.ascontiguousarray(offsets), arr
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    blob = np.frombuffer("".join(strings).encode("utf-32-le", "surrogatepass"), dtype=np.uint32).copy()
+    return blob, offsets, arr

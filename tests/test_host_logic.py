@@ -29,6 +29,20 @@ def test_pack_utf32_roundtrip():
         pack_utf32(["a", 3])
 
 
+def test_pack_strings_c_extension_equals_python_path():
+    from polyfuzz_b200 import strings
+    from polyfuzz_b200 import synth
+    assert strings._hostpack() is not None, "polyfuzz_b200/_pfz_hostpack*.so missing: run python -m polyfuzz_b200.build"
+    for lst in (synth.company_names(500, seed=1), synth.titles(500, seed=2) + ["", "İK", "a\U0001F600b"], ("tuple", "too"), []):
+        b, o = pack_utf32(list(lst))
+        b2, o2, _ = strings.pack_strings(lst)
+        assert np.array_equal(o, o2) and np.array_equal(b, b2.astype(np.uint32))
+        assert b2.dtype == (np.uint8 if all(s.isascii() for s in lst) and len(lst) else np.uint32)
+    for bad in (["a", None], ["a", 3]):
+        with pytest.raises(TypeError):
+            strings.pack_strings(bad)
+
+
 @pytest.mark.parametrize("rng", [(1, 1), (1, 3), (3, 3), (3, 6)])
 def test_slot_bounds_cover_every_ngram(rng):
     strs = ["apple", "", "a", "hello  world!!", "x" * 300, "İK"]
