@@ -13,6 +13,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """Built artefacts are git-ignored: (re)build the C-ABI library, the host packer and the CPU oracle when they are
+    missing or older than their sources (no-op on the GPU box, where the snapshot already carries them)."""
+    from polyfuzz_b200 import build as b
+    b.build(force=False)
+    from oracle import native
+    native.build()
+
+
 def pytest_collection_modifyitems(config, items):
     """GPU tests must never silently pass on a box without a GPU: they are skipped only when CUDA is
     absent AND -m gpu was not requested; with -m gpu on a GPU-less box they fail loudly."""
