@@ -242,6 +242,9 @@ def run_b200(args):
     total_ms = float(total_ms.item())
     k2_ms = [a.elapsed_time(b) for a, b in k2_events]
 
+    keep = {k: result[k] for k in ("vec", "csr", "index")}
+    result.clear(); result.update(keep)
+    gc.enable(); gc.collect(); gc.disable()
     # ---- leg 2: end to end through the public matcher API with HOST lists (e2e) -------------------
     def e2e_step():
         m = polyfuzz_b200.TFIDF(n_gram_range=(3, 3), min_similarity=0.0, top_n=TOP_N, distributed=world > 1)
@@ -266,6 +269,7 @@ def run_b200(args):
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
     e2e_ms_per_step = float(e2e_total.item()) / len(e2e_ms)
     gc.enable()
+    del df
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -313,7 +317,7 @@ def run_b200(args):
     h2d = staged_from.h2d_bytes * (1 if world == 1 else 2) + vec.n_vocab * 8
     d2h = n * TOP_N * 12 + vec.n_vocab * 12 + 4
     e2e = {"value": pairs / (e2e_ms_per_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": e2e_ms_per_step, "steps": len(e2e_ms),
+           "ms_per_step": e2e_ms_per_step, "steps": len(e2e_ms), "ms_each": [round(x, 2) for x in e2e_ms],
            "what": "TFIDF.match(list[str]) -> pandas.DataFrame: UTF-32 packing, H2D, K1, index, K2, D2H, frame assembly"}
 
     cpu = None

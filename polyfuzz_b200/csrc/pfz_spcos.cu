@@ -807,6 +807,9 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
     if (variant == PFZ_K2_DENSE32) {
         if (prune_alpha > 0.f && term_maxw) return launch(spcos_dense_kernel<WARPS, 4, true, true>, WARPS, (size_t)WARPS * arena_of(4));
         if (depth == 8) return launch(spcos_dense_kernel<WARPS, 8, true, false>, WARPS, (size_t)WARPS * arena_of(8));
+        if (depth == 6) return launch(spcos_dense_kernel<WARPS, 6, true, false>, WARPS, (size_t)WARPS * arena_of(6));
+        if (depth == 3) return launch(spcos_dense_kernel<WARPS, 3, true, false>, WARPS, (size_t)WARPS * arena_of(3));
+        if (depth == 2) return launch(spcos_dense_kernel<WARPS, 2, true, false>, WARPS, (size_t)WARPS * arena_of(2));
         return launch(spcos_dense_kernel<WARPS, 4, true, false>, WARPS, (size_t)WARPS * arena_of(4));
     }
     if (depth == 8) return launch(spcos_dense_kernel<WARPS, 8, false, false>, WARPS, (size_t)WARPS * arena_of(8));
