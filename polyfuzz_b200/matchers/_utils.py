@@ -70,9 +70,12 @@ def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarra
     if to_list is None:
         to_list = from_list
     n, k = top_idx.shape
-    sims_all = np.round(top_val, 3)
-    low_all = (sims_all < 0.001) | (top_idx < 0)
-    sims_all = np.where(low_all, 0.0, sims_all)
+    # column-major working copies: every per-column array below is contiguous
+    sims_t = np.round(np.ascontiguousarray(top_val.T), 3)
+    idx_t = np.ascontiguousarray(top_idx.T)
+    low_t = sims_t < 0.001
+    low_t |= idx_t < 0
+    sims_t[low_t] = 0.0
     names = ["To" if r == 0 else f"To_{r + 1}" for r in range(k)]
     snames = ["Similarity" if r == 0 else f"Similarity_{r + 1}" for r in range(k)]
     dt = _str_dtype()
@@ -83,13 +86,13 @@ def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarra
         cols["From"] = pd.Series(AT(from_pa, dtype=dt), copy=False)
 
         def gather(r):
-            ia = pa.array(np.where(low_all[:, r], 0, top_idx[:, r]), mask=np.ascontiguousarray(low_all[:, r]))
+            ia = pa.array(idx_t[r], mask=low_t[r])            # masked slots become nulls (their index value is ignored)
             return to_pa.take(ia)
 
         taken = list(_pool().map(gather, range(k))) if (k > 1 and n >= 20000) else [gather(r) for r in range(k)]
         for r in range(k):
             cols[names[r]] = pd.Series(AT(taken[r], dtype=dt), copy=False)
-            cols[snames[r]] = sims_all[:, r]
+            cols[snames[r]] = sims_t[r]
         return pd.DataFrame(cols, copy=False)
     # generic path (no Arrow-backed str dtype): object columns, explicit dtype so pandas infers nothing
     to_arr = np.empty(len(to_list) + 1, dtype=object)
@@ -97,7 +100,7 @@ def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarra
     to_arr[-1] = None
     cols["From"] = pd.Series(list(from_list), dtype=object)
     for r in range(k):
-        idx = np.where(low_all[:, r], len(to_list), top_idx[:, r].astype(np.int64))
+        idx = np.where(low_t[r], len(to_list), idx_t[r].astype(np.int64))
         cols[names[r]] = pd.Series(to_arr[idx], dtype=object)
-        cols[snames[r]] = sims_all[:, r]
+        cols[snames[r]] = sims_t[r]
     return pd.DataFrame(cols)
