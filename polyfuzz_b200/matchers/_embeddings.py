@@ -33,15 +33,17 @@ class Embeddings(BaseMatcher):
               embeddings_to: np.ndarray = None, re_train: bool = True) -> pd.DataFrame:
         """polyfuzz/models/_embeddings.py:87-135.  Rows are l2-normalised (as the reference's sklearn branch does,
         sk:metrics/pairwise.py:1744-1750; identical to its sparse branch for unit-norm inputs)."""
-        if not isinstance(embeddings_from, np.ndarray):
-            embeddings_from = self._embed(from_list)
-        if not isinstance(embeddings_to, np.ndarray):
-            if not re_train:
-                embeddings_to = self.embeddings_to
-            elif to_list is None:
-                embeddings_to = embeddings_from
-            else:
-                embeddings_to = self._embed(to_list)
+        given = lambda e: isinstance(e, np.ndarray)            # noqa: E731
+        vec_from = embeddings_from if given(embeddings_from) else self._embed(from_list)
+        if given(embeddings_to):
+            vec_to = embeddings_to
+        elif not re_train:
+            vec_to = self.embeddings_to                          # fitted earlier (PolyFuzz.transform)
+            if vec_to is None:
+                raise ValueError("re_train=False needs embeddings from an earlier match/fit")
+        else:
+            vec_to = vec_from if to_list is None else self._embed(to_list)
+        embeddings_from, embeddings_to = vec_from, vec_to
         top_n = clip_top_n(self.top_n, to_list)
         x, _ = dense.to_bf16_rows(embeddings_from, normalize=True)
         y = x if embeddings_to is embeddings_from else dense.to_bf16_rows(embeddings_to, normalize=True)[0]

@@ -116,3 +116,45 @@ def test_synth_generators_are_seeded():
     assert all(8 <= len(s) <= 32 for s in u)
     t = synth.titles(100, seed=1)
     assert len(t) == 100 and all(len(s) > 0 for s in t)
+
+
+def test_embeddings_matcher_control_flow_with_stubbed_kernels(monkeypatch):
+    """Host logic of Embeddings.match (which vectors are used when, fit/transform state, frame) with the two
+    device entry points replaced by numpy stand-ins -- the kernels themselves are covered by tests/test_gpu_dense.py."""
+    from polyfuzz_b200 import dense, Embeddings
+    calls = []
+
+    def fake_rows(x, normalize=True):
+        x = np.asarray(x, dtype=np.float64)
+        calls.append(x.shape)
+        return x / np.linalg.norm(x, axis=1, keepdims=True), None
+
+    def fake_topk(x, y, k, min_similarity=0.0, self_match=False, **kw):
+        s = x @ y.T
+        if self_match:
+            np.fill_diagonal(s, -np.inf)
+        idx = np.argsort(-s, axis=1, kind="stable")[:, :k]
+        val = np.take_along_axis(s, idx, 1)
+        idx = np.where(val > min_similarity, idx, -1); val = np.where(idx >= 0, val, 0.0)
+        return torch.from_numpy(idx.astype(np.int32)), torch.from_numpy(val)
+
+    monkeypatch.setattr(dense, "to_bf16_rows", fake_rows)
+    monkeypatch.setattr(dense, "dense_topk", fake_topk)
+    rng = np.random.default_rng(0)
+    ef, et = rng.normal(size=(4, 8)), rng.normal(size=(3, 8))
+    et[1] = ef[2] * 2.0
+    frm, to = ["a", "b", "c", "d"], ["x", "y", "z"]
+    m = Embeddings(min_similarity=0.0, top_n=2)
+    df = m.match(frm, to, ef, et)
+    assert list(df.columns) == ["From", "To", "Similarity", "To_2", "Similarity_2"] and df["To"][2] == "y" and df["Similarity"][2] == 1.0
+    assert m.embeddings_to is et and calls == [(4, 8), (3, 8)]
+    calls.clear()
+    df2 = m.match(["q"], to, ef[:1], re_train=False)                 # transform: reuses the fitted to-embeddings
+    assert calls == [(1, 8), (3, 8)] and len(df2) == 1
+    calls.clear()
+    df3 = m.match(frm, None, ef)                                      # self-match: one matrix for both sides
+    assert calls == [(4, 8)] and (df3["To"] != df3["From"]).all()
+    with pytest.raises(NotImplementedError):
+        Embeddings().match(frm, to)                                   # no vectors, no embedder
+    emb = Embeddings(embedding_method=lambda strs: rng.normal(size=(len(strs), 8)))
+    assert len(emb.match(frm, to)) == 4
