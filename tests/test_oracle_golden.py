@@ -161,3 +161,37 @@ def test_dense_fixture_vs_reference(golden_dir):
     for top_n in (1, 2, 3):
         idx, val = cosine_topk_dense(g["from_vec"], g["to_vec"], top_n, 0.0, normalize=True)
         np.testing.assert_array_equal(np.round(val, 3), g[f"sims_top{top_n}"])
+
+
+@pytest.mark.parametrize("k,ms,self_match", [(1, 0.0, False), (5, 0.2, False), (4, 0.0, True), (50, 0.0, False)])
+def test_two_oracle_statements_agree(k, ms, self_match):
+    """Gustavson (C) vs the dense fp64 statement, on TF-IDF rows of real-looking strings: same indices under the
+    canonical key; scores equal up to the different summation order of a dense dot product (<= 4 ulp)."""
+    from polyfuzz_b200 import synth
+    names = synth.company_names(700, seed=9) + ["dup co", "dup co", ""]
+    to = names if self_match else synth.company_names(400, seed=10) + ["dup co"]
+    f, t, _ = tfidf.fit_transform_sklearn(names, None if self_match else to)
+    kk = min(k, t.shape[0])
+    oi, ov = native.spdot_topn(f, t, kk, ms, self_match=self_match)
+    di, dv = cosine_topk_dense(f.toarray(), t.toarray(), kk, ms, self_match=self_match)
+    np.testing.assert_allclose(ov, dv, rtol=0, atol=1e-15)
+    # rows whose consecutive scores differ by more than the summation noise must agree index for index
+    gap = np.abs(np.diff(np.concatenate([dv, np.full((len(dv), 1), -1.0)], axis=1), axis=1))
+    stable = (gap > 1e-12).all(axis=1) & (np.abs(dv - ms) > 1e-12).all(axis=1)
+    assert stable.sum() > 50
+    np.testing.assert_array_equal(oi[stable], di[stable])
+
+
+def test_edit_distance_oracle_properties():
+    rng = np.random.default_rng(11)
+    alpha = "abcé中 "
+    s = ["".join(alpha[i] for i in rng.integers(0, len(alpha), rng.integers(0, 25))) for _ in range(60)]
+    d = native.editdist_matrix(s, s, "lev"); e = native.editdist_matrix(s, s, "indel")
+    la = np.array([len(x) for x in s])
+    assert (d == d.T).all() and (np.diag(d) == 0).all() and (e == e.T).all()
+    assert (d >= np.abs(la[:, None] - la[None, :])).all() and (d <= np.maximum(la[:, None], la[None, :])).all()
+    assert (e >= d).all() and (e <= 2 * d).all()                  # indel = lev with substitutions costed 2
+    assert ((e - np.abs(la[:, None] - la[None, :])) % 2 == 0).all()
+    # triangle inequality on a sample
+    for a, b, c in rng.integers(0, len(s), (200, 3)):
+        assert d[a, c] <= d[a, b] + d[b, c]
