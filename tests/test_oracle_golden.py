@@ -195,3 +195,31 @@ def test_edit_distance_oracle_properties():
     # triangle inequality on a sample
     for a, b, c in rng.integers(0, len(s), (200, 3)):
         assert d[a, c] <= d[a, b] + d[b, c]
+
+
+def test_fp32_filter_error_stays_below_half_the_margin():
+    """The mixed-precision K2 variant (dense32) relies on |fp32 sum - exact score| < MARGIN/2 = 1e-5 for rows of at
+    most 128 n-grams (polyfuzz_b200/engine.py: DENSE32_MAX_ROW_NNZ, csrc/pfz_spcos.cu: K2_MARGIN).  Emulate the fp32
+    accumulation (weights rounded to fp32, running sum in fp32, worst of several term orders) on real TF-IDF rows,
+    including rows close to the 128-term limit, and check the bound with room to spare."""
+    from polyfuzz_b200 import synth
+    rng = np.random.default_rng(4)
+    words = synth.company_names(300, seed=12)
+    long_rows = [" ".join(rng.choice(words, 6)) for _ in range(60)]          # ~100-128 distinct trigrams each
+    names = synth.company_names(1500, seed=13) + long_rows
+    a, _, _ = tfidf.fit_transform_sklearn(names)
+    nnz = np.diff(a.indptr)
+    assert nnz.max() > 100
+    keep = np.nonzero(nnz <= 128)[0]
+    dense = a[keep].toarray()
+    d32 = dense.astype(np.float32)
+    exact = dense @ dense.T
+    worst = 0.0
+    for trial in range(4):
+        perm = rng.permutation(dense.shape[1])
+        acc = np.zeros((len(keep), len(keep)), dtype=np.float32)
+        blocks = np.array_split(perm, 64)                                    # 64 sequential fp32 partial additions
+        for b in blocks:
+            acc = (acc + d32[:, b] @ d32[:, b].T).astype(np.float32)
+        worst = max(worst, float(np.abs(acc.astype(np.float64) - exact).max()))
+    assert worst < 5e-6, worst
