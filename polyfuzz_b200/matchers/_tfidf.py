@@ -2,11 +2,13 @@
 vectoriser (K1) and the sparse cosine top-n (K2) on a B200."""
 from typing import List, Tuple
 
+import os
+
 import numpy as np
 import pandas as pd
 
 from ._base import BaseMatcher
-from ._utils import assemble_matches, clip_top_n, prepare_strings
+from ._utils import assemble_matches, assemble_matches_chunked, clip_top_n, prepare_strings
 from .. import engine
 from ..distributed import get_comm, shard_bounds, tfidf_topk_sharded
 from ..strings import ARROW_CACHE
@@ -71,11 +73,44 @@ class TFIDF(BaseMatcher):
         whole from_list (diagonal excluded) -- one row-block of a self-match that is too large for one
         call / one GPU; the frame has hi-lo rows."""
         ARROW_CACHE.clear()
+        n_chunks = int(os.environ.get("PFZ_MATCH_CHUNKS", "1"))     # experimental (off): overlap scoring with assembly
+        if n_chunks > 1 and from_block is None and not (self.distributed and get_comm() is not None) and len(from_list) >= 20000:
+            return self._match_pipelined(from_list, to_list, re_train, n_chunks)
         top_idx, top_val, top_n = self.match_arrays(from_list, to_list, re_train, from_block)     # kernels are in flight
         rows = from_list if from_block is None else from_list[from_block[0]:from_block[1]]
         targets = to_list if to_list is not None else from_list
         prepared = prepare_strings(rows, targets if (to_list is not None or from_block is not None) else None)   # overlaps the GPU
         out = assemble_matches(rows, targets, top_idx.cpu().numpy(), top_val.cpu().numpy(), prepared=prepared)
+        ARROW_CACHE.clear()
+        return out
+
+    def _match_pipelined(self, from_list, to_list, re_train, n_chunks):
+        """EXPERIMENTAL (PFZ_MATCH_CHUNKS > 1; not validated on hardware in round 1): the from-rows are scored in
+        consecutive blocks; block b's top-k is copied to pinned host memory and assembled while the GPU scores block
+        b+1.  Results are identical to the one-shot path by construction (same kernels per row)."""
+        import torch
+        top_n = clip_top_n(self.top_n, to_list)
+        if top_n < 1:
+            raise ValueError("top_n must be >= 1 and to_list must not be empty")
+        tf_idf_from, _ = self._extract_tf_idf(from_list, to_list, re_train)
+        index = self._safe_index()
+        n = tf_idf_from.n_rows
+        bounds = [(b * n // n_chunks, (b + 1) * n // n_chunks) for b in range(n_chunks)]
+        pending = []
+        for lo, hi in bounds:
+            sub = engine.CsrMatrix(tf_idf_from.indptr[lo:hi + 1], tf_idf_from.indices, tf_idf_from.data, hi - lo, tf_idf_from.n_cols)
+            idx, val = engine.spcos_topk(sub, index, top_n, self.min_similarity, self_match=to_list is None, from_index_base=lo)
+            h_idx = torch.empty(idx.shape, dtype=idx.dtype, pin_memory=True); h_val = torch.empty(val.shape, dtype=val.dtype, pin_memory=True)
+            h_idx.copy_(idx, non_blocking=True); h_val.copy_(val, non_blocking=True)
+            ev = torch.cuda.Event(); ev.record()
+            pending.append((h_idx, h_val, ev))
+        targets = to_list if to_list is not None else from_list
+        prepared = prepare_strings(from_list, targets if to_list is not None else None)
+        chunks = []
+        for h_idx, h_val, ev in pending:
+            ev.synchronize()
+            chunks.append((h_idx.numpy(), h_val.numpy()))
+        out = assemble_matches_chunked(from_list, to_list, chunks, prepared=prepared)
         ARROW_CACHE.clear()
         return out
 
