@@ -286,9 +286,9 @@ __device__ __forceinline__ void rmw_posting(unsigned acc_s, unsigned flags_s, un
 // terms positive, exact sum <= 1), MARGIN = 2e-5.
 constexpr double K2_MARGIN = 2e-5;
 __device__ __forceinline__ void lds_item32(unsigned a, unsigned &off, int &cnt, float &v) {
-    unsigned vv, pad;
+    unsigned vv;
+    [[maybe_unused]] unsigned pad;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(off), "=r"(cnt), "=r"(vv), "=r"(pad) : "r"(a) : "memory");
-    (void)pad;
     v = __uint_as_float(vv);
 }
 __device__ __forceinline__ void ldg_posting32(const uint16_t *pi, const float *pv, int lane, int cnt, unsigned dummy, unsigned &jl, float &w) {
