@@ -106,6 +106,18 @@ def main():
     np.savez_compressed(os.path.join(HERE, "company_slice.npz"), **out)
     json.dump({"names": names}, open(os.path.join(HERE, "company_slice_names.json"), "w"))
 
+    # ---- movie titles slice (non-ASCII, punctuation): raw and clean vectoriser, (1,3)- and 3-grams ----------
+    mt = json.load(open(os.path.join(ref_shim.REFERENCE_ROOT, "data", "movie_titles.json")))
+    titles_to = mt["IMDB"][2000:2600]; titles_from = mt["Netflix"][:300]
+    out = {}
+    for tag, rng, clean in (("raw33", (3, 3), False), ("clean13", (1, 3), True), ("raw12", (1, 2), False)):
+        m = TFIDF(n_gram_range=rng, clean_string=clean, min_similarity=0, top_n=3, cosine_method="sklearn")
+        f, t = m._extract_tf_idf(titles_from, titles_to, True)
+        csr_parts(tag + "_from", f, out); csr_parts(tag + "_to", t, out)
+        out[tag + "_idf"] = m.vectorizer.idf_.astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "titles_slice.npz"), **out)
+    json.dump({"from": titles_from, "to": titles_to}, open(os.path.join(HERE, "titles_slice_names.json"), "w"))
+
     # ---- _clean_string exhaustive probe -----------------------------------------------------------
     surv = {}
     for cp in range(0x110000):

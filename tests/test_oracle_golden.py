@@ -223,3 +223,18 @@ def test_fp32_filter_error_stays_below_half_the_margin():
             acc = (acc + d32[:, b] @ d32[:, b].T).astype(np.float32)
         worst = max(worst, float(np.abs(acc.astype(np.float64) - exact).max()))
     assert worst < 5e-6, worst
+
+
+@pytest.mark.parametrize("tag,rng,clean", [("raw33", (3, 3), False), ("clean13", (1, 3), True), ("raw12", (1, 2), False)])
+def test_titles_slice_vectoriser_matches_reference(golden_dir, tag, rng, clean):
+    """Real movie titles (non-ASCII letters, punctuation, digits) from the reference's data/movie_titles.json:
+    both oracle statements reproduce the unmodified reference's CSR and idf bit for bit, raw and clean mode."""
+    g = np.load(os.path.join(golden_dir, "titles_slice.npz"))
+    names = json.load(open(os.path.join(golden_dir, "titles_slice_names.json")))
+    frm, to = names["from"], names["to"]
+    assert any(ord(c) > 127 for s in frm + to for c in s)
+    f, t, vec = tfidf.fit_transform_sklearn(frm, to, rng, clean, True)
+    _eq(f, g, tag + "_from"); _eq(t, g, tag + "_to")
+    o = tfidf.TfidfOracle(rng, clean, True).fit(list(to) + list(frm))
+    np.testing.assert_array_equal(o.idf, g[tag + "_idf"])
+    _eq(o.transform(frm), g, tag + "_from"); _eq(o.transform(to), g, tag + "_to")
