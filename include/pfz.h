@@ -43,6 +43,12 @@ int64_t     pfz_launch_count(void);
 /* device properties the host code needs for launch sizing: sm_count, max dynamic smem per block */
 int pfz_device_info(int32_t *sm_count, int32_t *smem_per_block_optin, int32_t *cc_major, int32_t *cc_minor);
 
+/* integer-ALU throughput probe: 8 independent LOP3/IADD chains per thread, sm_count*8 blocks of 256 threads,
+ * `iters` x 64 lane-ops per thread.  scratch: uint32[sm_count*8*256] on device.  *lane_ops_host receives the number of
+ * 32-bit lane-operations the launch executes; the caller times the launch (CUDA events) -> measured INT32 issue peak,
+ * the roofline denominator of K3 (bench.py).  Not on the product path.                                            */
+int pfz_int_alu_probe(int32_t iters, uint32_t *scratch, int64_t *lane_ops_host, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K1  char-n-gram TF-IDF vectoriser.
  * Replaces: polyfuzz/models/_tfidf.py:142-146 (_clean_string), :120-139 (_create_ngrams),

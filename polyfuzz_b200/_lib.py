@@ -16,6 +16,7 @@ _PROTOS = {
     "pfz_launch_count": [],
     "pfz_device_info": [c_vp, c_vp, c_vp, c_vp],
     "pfz_scan_ws_bytes": [c_i64],
+    "pfz_int_alu_probe": [c_i32, c_vp, c_vp, c_vp],
     "pfz_alphabet_mark": [c_vp, c_i64, c_vp, c_vp],
     "pfz_ngram_rows": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_u32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp],
     "pfz_df_dense": [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp],

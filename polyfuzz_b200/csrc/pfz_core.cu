@@ -76,9 +76,42 @@ int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, void *ws, cud
     PFZ_LAUNCH_OK();
     return 0;
 }
+
+// ---- integer-ALU throughput probe (the roofline denominator of K3, which is integer-issue bound) ------------
+// 8 independent chains per thread, each alternating LOP3 (xor3) and IADD -- the op mix of the bit-parallel recurrences.
+__global__ void __launch_bounds__(256) int_alu_probe_kernel(uint32_t *__restrict__ out, int iters, uint32_t seed) {
+    uint32_t a[8];
+    const uint32_t b = seed ^ (threadIdx.x * 2654435761u), c = seed * 3u + blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = b + i * 977u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(c));
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x ^= a[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
 }  // namespace pfz
 
 extern "C" {
+
+int pfz_int_alu_probe(int32_t iters, uint32_t *scratch, int64_t *lane_ops_host, void *stream) {
+    int dev = 0, sms = 0;
+    PFZ_CUDA_OK(cudaGetDevice(&dev));
+    PFZ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8;
+    pfz::int_alu_probe_kernel<<<blocks, 256, 0, pfz::as_stream(stream)>>>(scratch, iters, 12345u);
+    PFZ_LAUNCH_OK();
+    if (lane_ops_host) *lane_ops_host = (int64_t)blocks * 256 * (int64_t)iters * 64;
+    return 0;
+}
 
 int pfz_abi_version(void) { return PFZ_ABI_VERSION; }
 const char *pfz_last_error(void) { return pfz::g_err; }

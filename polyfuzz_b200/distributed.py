@@ -68,12 +68,16 @@ def get_comm(group=None):
 
 def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, top_n, min_similarity,
                        self_match, from_index_base=0, fit=True, fit_on_from=True, comm=None, index=None,
-                       tile=None, timings=None):
+                       tile=None, timings=None, k1_timings=None):
     """Sharded TF-IDF top-k.  Every rank passes the same from-list and its own to-shard.
     Returns (top_idx[n_from,k] GLOBAL indices, top_val[n_from,k], csr_to_shard, index)."""
     from . import engine
     if top_n > 32 and comm is not None:
         raise NotImplementedError("multi-GPU top_n > 32 is not supported yet")
+    ev1 = None
+    if k1_timings is not None:                              # K1 + index build, for bench.py's per-kernel breakdown
+        ev1 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev1[0].record()
     if fit:
         counted = [True, fit_on_from and (comm is None or comm.rank == 0)]
         staged = [staged_to_shard, staged_from]
@@ -91,6 +95,9 @@ def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, 
         csr_from = vectorizer.emit(vectorizer.rows(staged_from))
         if index.variant == "dense32" and vectorizer.max_row_nnz > engine.DENSE32_MAX_ROW_NNZ:
             index = engine.SparseIndex(index.csr, tile=tile, variant="dense")
+    if ev1 is not None:
+        ev1[1].record()
+        k1_timings.append(ev1)
     ev = None
     if timings is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))

@@ -1,4 +1,5 @@
-"""Parity at BASELINE.json's full sizes, through properties that do not need the oracle on the whole grid plus the
+"""Parity at BASELINE.json's full sizes ON THE REFERENCE'S OWN INPUTS (data/company_names.json and
+data/movie_titles.json travel as fixtures under tests/golden/data/), through properties that do not need the oracle on the whole grid plus the
 oracle on a sample of rows:
   config 2 (100k x 100k TF-IDF top-10): the three K2 kernels agree bit for bit; lists are sorted, duplicate-free and
       diagonal-free; scores are symmetric bit for bit (score(i,j) == score(j,i): same products, same order) and a row's
@@ -17,9 +18,10 @@ pytestmark = pytest.mark.gpu
 
 def test_config2_full_size_properties():
     import polyfuzz_b200
-    from polyfuzz_b200 import engine, synth
+    from polyfuzz_b200 import datasets, engine
     n, k = 100_000, 10
-    names = synth.company_names(n, seed=0)
+    names, kind = datasets.load_company_names(n)          # the reference's data/company_names.json (fixture)
+    assert kind == "real" and len(names) == n
     v = engine.NgramTfidf((3, 3), True, True)
     (rows,) = v.fit_rows([names]); csr = v.emit(rows)
     res = {}
@@ -55,8 +57,11 @@ def test_config2_full_size_properties():
 
 
 def test_config3_full_size_sample_and_symmetry():
-    from polyfuzz_b200 import editdist, synth
-    frm = synth.titles(6172, seed=1); to = synth.titles(80852, seed=2)
+    from polyfuzz_b200 import datasets, editdist
+    titles, kind = datasets.load_movie_titles()           # the reference's data/movie_titles.json (fixture)
+    assert kind == "real"
+    frm, to = titles["Netflix"], titles["IMDB"]
+    assert (len(frm), len(to)) == (6172, 80852)
     bi, bs, bd = editdist.edit_argbest(frm, to, "norm_lev")
     bi, bs, bd = bi.cpu().numpy(), bs.cpu().numpy(), bd.cpu().numpy()
     sel = np.random.default_rng(1).choice(len(frm), 48, replace=False)

@@ -341,3 +341,19 @@ def test_transform_after_pickle_with_unseen_and_empty_rows(pf, tmp_path):
     joblib.dump(m, tmp_path / "m.joblib")
     got = joblib.load(tmp_path / "m.joblib").match(new, to, re_train=False)
     assert got.equals(exp)
+
+
+@pytest.mark.parametrize("tag,rng,clean", [("raw33", (3, 3), False), ("clean13", (1, 3), True), ("raw12", (1, 2), False)])
+def test_titles_slice_vectoriser_matches_reference_on_gpu(pf, golden_dir, tag, rng, clean):
+    """Real movie titles (non-ASCII letters, punctuation, digits; raw and clean mode) from the reference's
+    data/movie_titles.json: K1 reproduces the unmodified reference's CSR and idf bit for bit (the CPU twin of this test,
+    tests/test_oracle_golden.py, pins the oracle on the same fixture)."""
+    _, engine = pf
+    g = np.load(os.path.join(golden_dir, "titles_slice.npz"))
+    names = json.load(open(os.path.join(golden_dir, "titles_slice_names.json")))
+    frm, to = names["from"], names["to"]
+    v = engine.NgramTfidf(rng, clean, True)
+    rows_to, rows_from = v.fit_rows([to, frm])
+    np.testing.assert_array_equal(v.idf, g[tag + "_idf"])
+    for name, rows in (("from", rows_from), ("to", rows_to)):
+        _csr_eq(v.emit(rows), g[f"{tag}_{name}_indptr"], g[f"{tag}_{name}_indices"], g[f"{tag}_{name}_data"], g[f"{tag}_{name}_shape"])
