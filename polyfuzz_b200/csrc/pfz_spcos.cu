@@ -56,38 +56,41 @@ __global__ void index_fill_kernel(const int32_t *__restrict__ indptr, const int3
 // most once, residues ascending, so a 16-lane window rarely holds two rows of the same bank
 // (random order: ~2.8 wavefronts per transaction; rounds: close to 1).
 constexpr int BANK_ORDER_MAX = 512;     // longer segments (only with very large tiles) keep their fill order
+// MOD = number of distinct shared-memory banks one accumulator word can fall into: 16 for the fp64 accumulators
+// (double-wide banks), 32 for the fp32 accumulators of the mixed-precision and from-row-block kernels.
+template <int MOD>
 __global__ void __launch_bounds__(128) index_bank_order_kernel(const int32_t *__restrict__ seg, int64_t ncell, uint16_t *__restrict__ post_idx,
                                                                double *__restrict__ post_val) {
     __shared__ uint16_t s_idx[4][BANK_ORDER_MAX];
     __shared__ uint16_t s_rank[4][BANK_ORDER_MAX];
     __shared__ double s_val[4][BANK_ORDER_MAX];
-    __shared__ int s_cnt[4][16];
+    __shared__ int s_cnt[4][MOD];
     const int lane = lane_id(), w = threadIdx.x >> 5;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t c0 = gw * 32; c0 < ncell; c0 += nw * 32) {
         // each lane inspects one cell, the warp then serves the cells that need work
         int s = 0, len = 0;
         if (c0 + lane < ncell) { s = seg[c0 + lane]; len = seg[c0 + lane + 1] - s; }
-        unsigned todo = __ballot_sync(FULL, len > 16 && len <= BANK_ORDER_MAX);
+        unsigned todo = __ballot_sync(FULL, len > MOD && len <= BANK_ORDER_MAX);
         while (todo) {
             const int src = __ffs(todo) - 1; todo &= todo - 1;
             const int cs = __shfl_sync(FULL, s, src), cl = __shfl_sync(FULL, len, src);
-            if (lane < 16) s_cnt[w][lane] = 0;
+            if (lane < MOD) s_cnt[w][lane] = 0;
             __syncwarp();
             for (int q = lane; q < cl; q += 32) {
                 const uint16_t j = post_idx[cs + q];
                 s_idx[w][q] = j; s_val[w][q] = post_val[cs + q];
-                s_rank[w][q] = (uint16_t)atomicAdd(&s_cnt[w][j & 15], 1);
+                s_rank[w][q] = (uint16_t)atomicAdd(&s_cnt[w][j & (MOD - 1)], 1);
             }
             __syncwarp();
-            int cnt[16];
+            int cnt[MOD];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) cnt[r] = s_cnt[w][r];
+            for (int r = 0; r < MOD; ++r) cnt[r] = s_cnt[w][r];
             for (int q = lane; q < cl; q += 32) {
-                const int r = s_idx[w][q] & 15, i = s_rank[w][q];
+                const int r = s_idx[w][q] & (MOD - 1), i = s_rank[w][q];
                 int pos = 0;
 #pragma unroll
-                for (int r2 = 0; r2 < 16; ++r2) pos += min(cnt[r2], i) + ((r2 < r && cnt[r2] > i) ? 1 : 0);
+                for (int r2 = 0; r2 < MOD; ++r2) pos += min(cnt[r2], i) + ((r2 < r && cnt[r2] > i) ? 1 : 0);
                 post_idx[cs + pos] = s_idx[w][q];
                 post_val[cs + pos] = s_val[w][q];
             }
@@ -283,8 +286,9 @@ __device__ __forceinline__ void rmw_posting(unsigned acc_s, unsigned flags_s, un
 // thr - MARGIN, and every flagged row is re-scored exactly -- fp64, ascending term order, products rounded
 // before the add -- by merging the two CSR rows, so the ranking and the returned scores are the canonical
 // ones bit for bit.  |fp32 sum - exact| <= ~70 * 2^-24 + 3 * 2^-24 < 5e-6 for l2-normalised rows (all
-// terms positive, exact sum <= 1), MARGIN = 2e-5.
-constexpr double K2_MARGIN = 2e-5;
+// terms positive, exact sum <= 1) with ~70 terms; rows of up to 128 terms (engine.DENSE32_MAX_ROW_NNZ) stay below 7.7e-6, and the
+// k-th gate compares two fp32 sums (<= 1.55e-5 combined): MARGIN = 3e-5 leaves a factor of two.
+constexpr double K2_MARGIN = 3e-5;
 __device__ __forceinline__ void lds_item32(unsigned a, unsigned &off, int &cnt, float &v) {
     unsigned vv;
     [[maybe_unused]] unsigned pad;
@@ -746,8 +750,11 @@ int pfz_index_build(const int32_t *indptr, const int32_t *indices, const double 
         index_fill_kernel<<<grid_for2((int64_t)n_rows * 32, 256, 148 * 16), 256, 0, st>>>(indptr, indices, data, n_rows, tile, n_tiles, seg, cur,
                                                                                             post_idx, post_val, reinterpret_cast<int *>(term_maxw));
         PFZ_LAUNCH_OK();
-        if (flags & PFZ_INDEX_BANK_ORDER) {
-            index_bank_order_kernel<<<grid_for2(ncell, 128, 148 * 16), 128, 0, st>>>(seg, ncell, post_idx, post_val);
+        if (flags & PFZ_INDEX_BANK_ORDER32) {
+            index_bank_order_kernel<32><<<grid_for2(ncell, 128, 148 * 16), 128, 0, st>>>(seg, ncell, post_idx, post_val);
+            PFZ_LAUNCH_OK();
+        } else if (flags & PFZ_INDEX_BANK_ORDER) {
+            index_bank_order_kernel<16><<<grid_for2(ncell, 128, 148 * 16), 128, 0, st>>>(seg, ncell, post_idx, post_val);
             PFZ_LAUNCH_OK();
         }
         if (post_val32) {                                       // fp32 copy of the weights for the mixed-precision filter

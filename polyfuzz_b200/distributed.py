@@ -93,7 +93,7 @@ def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, 
     else:
         csr_to = None
         csr_from = vectorizer.emit(vectorizer.rows(staged_from))
-        if index.variant == "dense32" and vectorizer.max_row_nnz > engine.DENSE32_MAX_ROW_NNZ:
+        if index.variant in ("dense32", "block") and vectorizer.max_row_nnz > engine.DENSE32_MAX_ROW_NNZ:
             index = engine.SparseIndex(index.csr, tile=tile, variant="dense")
     if ev1 is not None:
         ev1[1].record()

@@ -201,7 +201,6 @@ class NgramTfidf:
 
     # ---- stage A ----------------------------------------------------------------------------------
     def _stage_a(self, S, d_sym):
-        self.max_row_nnz = max(self.max_row_nnz, S.max_slots)
         R = _Rows()
         R.n, R.cap, R.occ_ptr = S.n, S.cap, S.occ_ptr
         R.codes = torch.empty(max(R.cap, 1), dtype=torch.int64, device=_dev())
@@ -211,6 +210,12 @@ class NgramTfidf:
                   int(self.base), _p(R.occ_ptr), _p(S.d_long), S.n_long, _p(R.codes), _p(R.tf), _p(R.row_cnt),
                   _stream())
         R._keep = S
+        # upper bound of any row's nnz: the host-side slot bound, tightened to the true maximum (one small D2H) only when
+        # the bound alone would rule out the fp32-filter kernels
+        bound = S.max_slots
+        if bound > DENSE32_MAX_ROW_NNZ and R.n:
+            bound = int(R.row_cnt[:R.n].max().item())
+        self.max_row_nnz = max(self.max_row_nnz, bound)
         return R
 
     def _fit_alphabet(self, staged, comm=None):
@@ -354,7 +359,8 @@ class NgramTfidf:
 # to-tile rows per K2 variant: the list kernel wants many small per-warp arenas (occupancy), the dense
 # kernel few large ones (long segments; it pipelines its own loads)
 DEFAULT_TILE = {"list": int(os.environ.get("PFZ_TILE_LIST", "512")), "dense": int(os.environ.get("PFZ_TILE_DENSE", "1024")),
-                "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1024"))}
+                "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1024")), "block": int(os.environ.get("PFZ_TILE_BLOCK", "1024"))}
+BLOCK_TILE_STEP, BLOCK_TILE_MAX = 128, 2048
 
 
 class SparseIndex:
@@ -366,6 +372,8 @@ class SparseIndex:
         if tile is None:
             tile = DEFAULT_TILE[variant]
         tile = max(64, min(int(tile), ((max(n, 1) + 63) // 64) * 64))
+        if variant == "block":                                # the block kernel scans its accumulators 128 cells per warp step
+            tile = min(BLOCK_TILE_MAX, max(BLOCK_TILE_STEP, (tile + BLOCK_TILE_STEP - 1) // BLOCK_TILE_STEP * BLOCK_TILE_STEP))
         self.tile = tile
         self.n_to = n
         self.n_vocab = csr.n_cols
@@ -376,13 +384,19 @@ class SparseIndex:
         cap = max(csr.indices.numel(), 1)
         self.post_idx = torch.empty(cap, dtype=torch.int16, device=dev)          # uint16 tile-local row
         self.post_val = torch.empty(cap, dtype=torch.float64, device=dev)
-        self.post_val32 = torch.empty(cap, dtype=torch.float32, device=dev) if variant == "dense32" else None
+        f32 = variant in ("dense32", "block")
+        self.post_val32 = torch.empty(cap, dtype=torch.float32, device=dev) if f32 else None
         self.term_maxw = torch.empty(max(self.n_vocab, 1), dtype=torch.float32, device=dev) if variant == "dense32" else None
-        self.csr = csr                                          # the to-matrix itself (exact re-scoring in dense32)
+        self.post_pk = torch.empty((cap, 2), dtype=torch.int32, device=dev) if variant == "block" else None   # {tile-local row, fp32 weight bits}
+        self.csr = csr                                          # the to-matrix itself (exact re-scoring in dense32 / block)
         ws = _ws((ncell + 1) * 4 + 512 + _lib.load().pfz_scan_ws_bytes(ncell + 1))
-        flags = 1 if os.environ.get("PFZ_BANK_ORDER", "1") != "0" else 0
+        flags = 0
+        if os.environ.get("PFZ_BANK_ORDER", "1") != "0":
+            flags = 2 if f32 else 1                             # 32 four-byte banks for fp32 accumulators, 16 eight-byte banks for fp64
         _lib.call("pfz_index_build", _p(csr.indptr), _p(csr.indices), _p(csr.data), n, self.n_vocab, tile,
                   self.n_tiles, flags, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(self.post_val32), _p(self.term_maxw), _p(ws), _stream())
+        if variant == "block" and n > 0:
+            _lib.call("pfz_index_pack32", _p(self.post_idx), _p(self.post_val32), ctypes.c_void_p(self.seg.data_ptr() + 4 * ncell), _p(self.post_pk), _stream())
 
 
 DENSE32_MAX_ROW_NNZ = 128
@@ -395,7 +409,7 @@ def choose_variant(density, max_row_nnz=None):
     so rows longer than DENSE32_MAX_ROW_NNZ n-grams select the plain fp64 `dense` kernel."""
     if density is None or density < DENSE_MIN_DENSITY:
         return "list"
-    if DENSE_VARIANT == "dense32" and (max_row_nnz is None or max_row_nnz > DENSE32_MAX_ROW_NNZ):
+    if DENSE_VARIANT in ("dense32", "block") and (max_row_nnz is None or max_row_nnz > DENSE32_MAX_ROW_NNZ):
         return "dense"
     return DENSE_VARIANT
 
@@ -409,8 +423,31 @@ def _auto_splits(n_from, n_tiles, sm_count=148):
 
 K2_LIST, K2_DENSE, K2_DENSE32 = 1, 2, 3
 DENSE_MIN_DENSITY = float(os.environ.get("PFZ_DENSE_MIN_DENSITY", "0.03"))
-DENSE_VARIANT = os.environ.get("PFZ_DENSE_VARIANT", "dense32")   # which kernel serves the dense regime
+DENSE_VARIANT = os.environ.get("PFZ_DENSE_VARIANT", "block")     # which kernel serves the dense regime
 K2_VARIANT = {"list": K2_LIST, "dense": K2_DENSE, "dense32": K2_DENSE32}
+BLOCK_MAX_ROWS = (1 << 22) - 1                                   # row id field of the block kernel's clustering key
+
+
+def _spcos_block(a, index, k, min_similarity, self_match, from_index_base, to_index_base, n_splits):
+    """from-row-block kernel (pfz_spcos_topk_block): clustering + block tables + scoring, all enqueued on the stream."""
+    dev = _dev()
+    n_from = a.n_rows
+    nnz_cap = int(a.indices.numel())
+    ws = _ws(_lib.load().pfz_spcos_block_ws_bytes(n_from, nnz_cap, index.n_vocab, n_splits))
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    ti = torch.empty((n_splits, max(n_from, 1), k), dtype=torch.int32, device=dev)
+    tv = torch.empty((n_splits, max(n_from, 1), k), dtype=torch.float64, device=dev)
+    _lib.call("pfz_spcos_topk_block", _p(a.indptr), _p(a.indices), _p(a.data), n_from, nnz_cap, _p(index.seg), _p(index.post_pk),
+              _p(index.csr.indptr), _p(index.csr.indices), _p(index.csr.data), index.n_vocab, index.tile, index.n_tiles, index.n_to, k,
+              float(min_similarity), int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, _p(ti), _p(tv), _p(err),
+              _p(ws), _stream())
+    if n_splits > 1:
+        oi = torch.empty((max(n_from, 1), k), dtype=torch.int32, device=dev)
+        ov = torch.empty((max(n_from, 1), k), dtype=torch.float64, device=dev)
+        _lib.call("pfz_topk_merge", _p(ti), _p(tv), n_splits, n_from, k, k, _p(oi), _p(ov), _stream())
+    else:
+        oi, ov = ti[0], tv[0]
+    return oi[:n_from], ov[:n_from], err
 
 
 def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_match=False, from_index_base=0,
@@ -428,6 +465,14 @@ def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_mat
     if n_splits is None:
         n_splits = _auto_splits(n_from, index.n_tiles)
     n_splits = max(1, min(int(n_splits), index.n_tiles))
+    if variant == "block":
+        if index.post_pk is None:
+            raise ValueError("the index was not built for the block variant")
+        if k <= 32 and n_from <= BLOCK_MAX_ROWS and index.n_to < (1 << 28):
+            oi, ov, err = _spcos_block(a, index, k, min_similarity, self_match, from_index_base, to_index_base, n_splits)
+            index._block_err = err                         # non-zero iff a from-row exceeded 128 terms (callers pick the variant so that it cannot)
+            return oi, ov
+        variant = "dense32"                                # paging (top_n > 32) runs on the per-row kernel over the same index
     counter = torch.zeros(n_splits, dtype=torch.int32, device=dev)
     pages = []
     excl_v = excl_i = None

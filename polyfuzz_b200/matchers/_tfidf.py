@@ -196,7 +196,7 @@ class TFIDF(BaseMatcher):
     def _safe_index(self):
         """A later transform() may bring from-rows longer than the mixed-precision bound allows: rebuild the
         index for the fp64 kernel then (the to-matrix is unchanged)."""
-        if self._index.variant == "dense32" and self.vectorizer.max_row_nnz > engine.DENSE32_MAX_ROW_NNZ:
+        if self._index.variant in ("dense32", "block") and self.vectorizer.max_row_nnz > engine.DENSE32_MAX_ROW_NNZ:
             self._index = engine.SparseIndex(self._device_to(), variant="dense")
         return self._index
 

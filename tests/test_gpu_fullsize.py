@@ -25,10 +25,10 @@ def test_config2_full_size_properties():
     v = engine.NgramTfidf((3, 3), True, True)
     (rows,) = v.fit_rows([names]); csr = v.emit(rows)
     res = {}
-    for variant, tile in (("dense32", None), ("dense", None), ("list", None)):
+    for variant, tile in (("block", None), ("dense32", None), ("dense", None), ("list", None)):
         ix = engine.SparseIndex(csr, tile=tile, variant=variant)
         res[variant] = engine.spcos_topk(csr, ix, k, 0.0, self_match=True)
-    for variant in ("dense", "list"):
+    for variant in ("block", "dense", "list"):
         assert torch.equal(res[variant][0], res["dense32"][0]) and torch.equal(res[variant][1], res["dense32"][1]), variant
     idx = res["dense32"][0].cpu().numpy(); val = res["dense32"][1].cpu().numpy()
     valid = idx >= 0

@@ -106,7 +106,7 @@ def test_company_slice_vectoriser_bit_exact(pf, company):
     _csr_eq(v.emit(rows), g["csr_indptr"], g["csr_indices"], g["csr_data"], g["csr_shape"])
 
 
-@pytest.mark.parametrize("variant", ["list", "dense", "dense32"])
+@pytest.mark.parametrize("variant", ["list", "dense", "dense32", "block"])
 @pytest.mark.parametrize("tile", [None, 256, 1024])
 @pytest.mark.parametrize("n_splits", [1, 3])
 def test_company_slice_topk_vs_oracle_and_reference(pf, company, tile, n_splits, variant):
@@ -156,10 +156,11 @@ def _oracle_two(frm, to, rng=(3, 3), clean=True, rs=True):
 def _force_variant(monkeypatch, engine, variant):
     monkeypatch.setattr(engine, "DENSE_MIN_DENSITY", 1e9 if variant == "list" else 0.0)
     monkeypatch.setattr(engine, "DENSE_VARIANT", variant if variant != "list" else "dense")
-    monkeypatch.setattr(engine, "DENSE32_MAX_ROW_NNZ", 1 << 30)        # exercise the filter even on long rows
+    if variant != "block":                                             # (the block kernel's tables hold <= 128 terms per row)
+        monkeypatch.setattr(engine, "DENSE32_MAX_ROW_NNZ", 1 << 30)    # exercise the filter even on long rows
 
 
-@pytest.mark.parametrize("variant", ["list", "dense", "dense32"])
+@pytest.mark.parametrize("variant", ["list", "dense", "dense32", "block"])
 @pytest.mark.parametrize("k,ms", [(1, 0.0), (5, 0.3), (32, 0.0), (40, 0.0), (70, 0.05)])
 def test_synthetic_two_list_vs_oracle(pf, k, ms, variant, monkeypatch):
     polyfuzz_b200, engine = pf
@@ -242,7 +243,7 @@ def test_from_block_is_a_row_block_of_the_self_match(pf):
     assert blk.reset_index(drop=True).equals(full.iloc[1000:1800].reset_index(drop=True))
 
 
-@pytest.mark.parametrize("variant", ["list", "dense", "dense32"])
+@pytest.mark.parametrize("variant", ["list", "dense", "dense32", "block"])
 def test_every_row_shares_many_heavy_terms(pf, variant, monkeypatch):
     """All rows share ~20 trigrams, so every (term, tile) segment is the full tile: per-unit work far
     exceeds the dense kernel's work-item table (batched consumption) and every accumulator gets ~20
@@ -280,11 +281,12 @@ def test_shard_emulation_equals_unsharded(pf):
     assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
 
 
-def test_dense32_many_exact_ties_and_identical_rows(pf, monkeypatch):
+@pytest.mark.parametrize("variant", ["dense32", "block"])
+def test_dense32_many_exact_ties_and_identical_rows(pf, monkeypatch, variant):
     """The fp32 filter must hand every row near the k-th key to the exact re-scoring: lists full of duplicates
     (scores exactly 1.0 and large groups of exactly tied scores)."""
     polyfuzz_b200, engine = pf
-    _force_variant(monkeypatch, engine, "dense32")
+    _force_variant(monkeypatch, engine, variant)
     names = ["acme holdings inc"] * 40 + ["acme holding inc"] * 40 + [f"zeta {i % 5} llc" for i in range(300)] + ["unique name ltd"]
     m = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=12)
     idx, val, k = m.match_arrays(names)
@@ -357,3 +359,27 @@ def test_titles_slice_vectoriser_matches_reference_on_gpu(pf, golden_dir, tag, r
     np.testing.assert_array_equal(v.idf, g[tag + "_idf"])
     for name, rows in (("from", rows_from), ("to", rows_to)):
         _csr_eq(v.emit(rows), g[f"{tag}_{name}_indptr"], g[f"{tag}_{name}_indices"], g[f"{tag}_{name}_data"], g[f"{tag}_{name}_shape"])
+
+
+def test_block_variant_long_rows_split_blocks_and_margin(pf, monkeypatch):
+    """The from-row-block kernel at its contract's edge: rows of ~100-128 distinct trigrams (blocks of 8 such rows exceed the
+    512-entry block table and are split in halves), mixed with short rows, duplicates and empty rows; tile 128 and a tile
+    split.  The fp32 filter (margin 3e-5) must still hand every contender to the exact re-scoring."""
+    polyfuzz_b200, engine = pf
+    from polyfuzz_b200 import synth
+    rng = np.random.default_rng(5)
+    words = synth.company_names(400, seed=12)
+    long_rows = [" ".join(rng.choice(words, 5)) for _ in range(300)]
+    names = synth.company_names(2000, seed=13) + long_rows + ["", "ab", long_rows[0], long_rows[0] + " x"]
+    v = engine.NgramTfidf((3, 3), True, True)
+    (rows,) = v.fit_rows([names]); csr = v.emit(rows)
+    a = csr.to_scipy()
+    nnz = np.diff(a.indptr)
+    assert 100 < nnz.max() <= 128, nnz.max()
+    oi, ov = onative.spdot_topn(a, a, 10, 0.0, self_match=True, n_threads=8)
+    for tile, splits in ((128, 1), (1024, 1), (512, 3)):
+        ix = engine.SparseIndex(csr, tile=tile, variant="block")
+        idx, val = engine.spcos_topk(csr, ix, 10, 0.0, self_match=True, n_splits=splits)
+        assert int(ix._block_err.item()) == 0
+        np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+        np.testing.assert_array_equal(val.cpu().numpy(), ov)
