@@ -161,21 +161,22 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
                    int32_t *top_idx, double *top_val, int32_t *row_counter, int32_t variant, void *stream);
 
 /* PFZ_K2_BLOCK -- from-row-block variant of K2 (csrc/pfz_spcos_block.cu): the from-rows are clustered by their heaviest
- * terms and scored 8 at a time, so one load of a posting chunk serves every row of the block that contains the term; fp32
- * shared-memory sums filter, flagged cells are re-scored exactly from the two CSR rows (as PFZ_K2_DENSE32): indices and
- * scores are bit-identical to the other variants.  Same reference call site (polyfuzz/models/_utils.py:82).
- *   post_pk: uint2[nnz] = {tile-local row, fp32 weight bits} in segment order (pfz_index_pack32 of an index built with
- *            post_val32 and PFZ_INDEX_BANK_ORDER32); tile: multiple of 128, <= 2048; k <= 32; from-rows <= 128 terms each
- *            (*err_flag_dev is set to 1 otherwise); n_from < 2^22, n_to < 2^28.
+ * terms and scored block_rows (8 or 16) at a time by one CTA, so one load of a posting chunk serves every row of the block
+ * that contains the term; 32-bit fixed-point sums in shared memory (red.shared.add.u32) filter, flagged cells are re-scored
+ * exactly from the two CSR rows (as PFZ_K2_DENSE32): indices and scores are bit-identical to the other variants.  Same
+ * reference call site (polyfuzz/models/_utils.py:82).
+ *   post_pk: uint2[nnz] = {tile-local row, round(weight * 2^26)} in segment order (pfz_index_pack_q26 of an index built with
+ *            PFZ_INDEX_BANK_ORDER32); tile: multiple of 128; k <= 32; from-rows <= 128 terms each (*err_flag_dev is set to 1
+ *            otherwise); n_from < 2^22.
  *   nnz_cap_from: capacity of a_indices / a_data (>= nnz).  ws: >= pfz_spcos_block_ws_bytes(...) bytes.
  *   Output as pfz_spcos_topk: [n_splits][n_from][k] partial lists (pfz_topk_merge when n_splits > 1).                    */
 int64_t pfz_spcos_block_ws_bytes(int32_t n_from, int64_t nnz_cap_from, int32_t n_vocab, int32_t n_splits);
-int pfz_index_pack32(const uint16_t *post_idx, const float *post_val32, const int32_t *nnz_dev, void *post_pk, void *stream);
+int pfz_index_pack_q26(const uint16_t *post_idx, const double *post_val, const int32_t *nnz_dev, void *post_pk, void *stream);
 int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from, int64_t nnz_cap_from,
                          const int32_t *seg, const void *post_pk, const int32_t *b_indptr, const int32_t *b_indices, const double *b_data,
                          int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to, int32_t k, double min_similarity, int32_t self_match,
-                         int64_t from_index_base, int64_t to_index_base, int32_t n_splits, int32_t *top_idx, double *top_val,
-                         int32_t *err_flag_dev, void *ws, void *stream);
+                         int64_t from_index_base, int64_t to_index_base, int32_t n_splits, int32_t block_rows, int32_t *top_idx,
+                         double *top_val, int32_t *err_flag_dev, void *ws, void *stream);
 
 /* merge n_lists sorted top-k lists per row ([n_lists][n_from][k_in]) into [n_from][k_out];
  * same key.  Used for tile splits and for the per-shard lists after the NCCL all-gather.            */

@@ -360,7 +360,8 @@ class NgramTfidf:
 # kernel few large ones (long segments; it pipelines its own loads)
 DEFAULT_TILE = {"list": int(os.environ.get("PFZ_TILE_LIST", "512")), "dense": int(os.environ.get("PFZ_TILE_DENSE", "1024")),
                 "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1024")), "block": int(os.environ.get("PFZ_TILE_BLOCK", "1024"))}
-BLOCK_TILE_STEP, BLOCK_TILE_MAX = 128, 2048
+BLOCK_TILE_STEP, BLOCK_TILE_MAX = 128, 4096
+BLOCK_ROWS = int(os.environ.get("PFZ_BLOCK_ROWS", "8"))           # from-rows (= warps) per CTA of the block kernel: 8 or 16
 
 
 class SparseIndex:
@@ -387,7 +388,7 @@ class SparseIndex:
         f32 = variant in ("dense32", "block")
         self.post_val32 = torch.empty(cap, dtype=torch.float32, device=dev) if f32 else None
         self.term_maxw = torch.empty(max(self.n_vocab, 1), dtype=torch.float32, device=dev) if variant == "dense32" else None
-        self.post_pk = torch.empty((cap, 2), dtype=torch.int32, device=dev) if variant == "block" else None   # {tile-local row, fp32 weight bits}
+        self.post_pk = torch.empty((cap, 2), dtype=torch.int32, device=dev) if variant == "block" else None   # {tile-local row, round(weight * 2^26)}
         self.csr = csr                                          # the to-matrix itself (exact re-scoring in dense32 / block)
         ws = _ws((ncell + 1) * 4 + 512 + _lib.load().pfz_scan_ws_bytes(ncell + 1))
         flags = 0
@@ -396,7 +397,7 @@ class SparseIndex:
         _lib.call("pfz_index_build", _p(csr.indptr), _p(csr.indices), _p(csr.data), n, self.n_vocab, tile,
                   self.n_tiles, flags, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(self.post_val32), _p(self.term_maxw), _p(ws), _stream())
         if variant == "block" and n > 0:
-            _lib.call("pfz_index_pack32", _p(self.post_idx), _p(self.post_val32), ctypes.c_void_p(self.seg.data_ptr() + 4 * ncell), _p(self.post_pk), _stream())
+            _lib.call("pfz_index_pack_q26", _p(self.post_idx), _p(self.post_val), ctypes.c_void_p(self.seg.data_ptr() + 4 * ncell), _p(self.post_pk), _stream())
 
 
 DENSE32_MAX_ROW_NNZ = 128
@@ -439,7 +440,7 @@ def _spcos_block(a, index, k, min_similarity, self_match, from_index_base, to_in
     tv = torch.empty((n_splits, max(n_from, 1), k), dtype=torch.float64, device=dev)
     _lib.call("pfz_spcos_topk_block", _p(a.indptr), _p(a.indices), _p(a.data), n_from, nnz_cap, _p(index.seg), _p(index.post_pk),
               _p(index.csr.indptr), _p(index.csr.indices), _p(index.csr.data), index.n_vocab, index.tile, index.n_tiles, index.n_to, k,
-              float(min_similarity), int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, _p(ti), _p(tv), _p(err),
+              float(min_similarity), int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, BLOCK_ROWS, _p(ti), _p(tv), _p(err),
               _p(ws), _stream())
     if n_splits > 1:
         oi = torch.empty((max(n_from, 1), k), dtype=torch.int32, device=dev)
@@ -468,7 +469,7 @@ def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_mat
     if variant == "block":
         if index.post_pk is None:
             raise ValueError("the index was not built for the block variant")
-        if k <= 32 and n_from <= BLOCK_MAX_ROWS and index.n_to < (1 << 28):
+        if k <= 32 and n_from <= BLOCK_MAX_ROWS:
             oi, ov, err = _spcos_block(a, index, k, min_similarity, self_match, from_index_base, to_index_base, n_splits)
             index._block_err = err                         # non-zero iff a from-row exceeded 128 terms (callers pick the variant so that it cannot)
             return oi, ov

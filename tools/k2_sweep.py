@@ -1,13 +1,13 @@
-"""Developer tool: time K1 stages and K2 over tile sizes on the synthetic company-names workload."""
+"""Developer tool: time K1 stages and K2 over tile sizes on the company-names workload (real fixture when present)."""
 import sys, os, time
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import numpy as np
 import torch
-from polyfuzz_b200 import engine, synth
+from polyfuzz_b200 import datasets, engine
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
 tiles = [int(t) for t in sys.argv[2].split(",")] if len(sys.argv) > 2 else [512, 1024, 1536, 2048, 2560, 2816]
-names = synth.company_names(n, seed=0)
+names, _kind = datasets.load_company_names(n)
 torch.cuda.init()
 
 
