@@ -178,6 +178,21 @@ int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, cons
                          int64_t from_index_base, int64_t to_index_base, int32_t n_splits, int32_t block_rows, int32_t *top_idx,
                          double *top_val, int32_t *err_flag_dev, void *ws, void *stream);
 
+/* PFZ_K2_HASH -- sparse-regime variant of K2 (csrc/pfz_spcos_hash.cu): one CTA per from-row accumulates the postings the row
+ * visits in a shared-memory hash table keyed by the to-row (atom.shared.cas + red.shared.add.u32, fixed point 2^-26), scans
+ * the table once and re-scores the sums above the row's threshold exactly; work ~ postings, independent of n_tiles.  For
+ * inputs where a from-row touches a small fraction of the to-rows (uniform text).  Same reference call site
+ * (polyfuzz/models/_utils.py:82), bit-identical results.
+ *   index: built with tile = 65536 (the largest the 16-bit local rows allow) + pfz_index_pack_q26; from-rows <= 256 terms.
+ *   table_slots: 2048 | 8192 | 16384; a row whose postings exceed half the table is scored in several tile-range passes;
+ *   *err_flag_dev: 2 = table overflow (a single tile held more postings than the table), 3 = row longer than 256 terms.
+ *   excl_val/excl_idx: as pfz_spcos_topk (paging).  Output [n_splits][n_from][k].                                        */
+int pfz_spcos_topk_hash(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from, const int32_t *seg,
+                        const void *post_pk, const int32_t *b_indptr, const int32_t *b_indices, const double *b_data, int32_t tile,
+                        int32_t n_tiles, int32_t n_to, int32_t k, double min_similarity, int32_t self_match, int64_t from_index_base,
+                        int64_t to_index_base, int32_t n_splits, int32_t table_slots, const double *excl_val, const int32_t *excl_idx,
+                        int32_t *top_idx, double *top_val, int32_t *row_counter, int32_t *err_flag_dev, void *stream);
+
 /* merge n_lists sorted top-k lists per row ([n_lists][n_from][k_in]) into [n_from][k_out];
  * same key.  Used for tile splits and for the per-shard lists after the NCCL all-gather.            */
 int pfz_topk_merge(const int32_t *idx, const double *val, int32_t n_lists, int32_t n_from, int32_t k_in,

@@ -88,13 +88,15 @@ def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, 
         else:
             rows_to, rows_from = vectorizer.fit_staged(staged, counted=counted, comm=comm)
         csr_to = vectorizer.emit(rows_to)
-        index = engine.SparseIndex(csr_to, tile=tile, variant=engine.choose_variant(vectorizer.density(), vectorizer.max_row_nnz))
+        index = engine.SparseIndex(csr_to, tile=tile, variant=engine.choose_variant(vectorizer.density(), vectorizer.max_row_nnz, csr_to.n_rows))
         csr_from = csr_to if same else vectorizer.emit(rows_from)
     else:
         csr_to = None
         csr_from = vectorizer.emit(vectorizer.rows(staged_from))
         if index.variant in ("dense32", "block") and vectorizer.max_row_nnz > engine.DENSE32_MAX_ROW_NNZ:
             index = engine.SparseIndex(index.csr, tile=tile, variant="dense")
+        elif index.variant == "hash" and vectorizer.max_row_nnz > engine.HASH_MAX_ROW_NNZ:
+            index = engine.SparseIndex(index.csr, tile=tile, variant="list")
     if ev1 is not None:
         ev1[1].record()
         k1_timings.append(ev1)

@@ -359,7 +359,8 @@ class NgramTfidf:
 # to-tile rows per K2 variant: the list kernel wants many small per-warp arenas (occupancy), the dense
 # kernel few large ones (long segments; it pipelines its own loads)
 DEFAULT_TILE = {"list": int(os.environ.get("PFZ_TILE_LIST", "512")), "dense": int(os.environ.get("PFZ_TILE_DENSE", "1024")),
-                "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1024")), "block": int(os.environ.get("PFZ_TILE_BLOCK", "1024"))}
+                "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1024")), "block": int(os.environ.get("PFZ_TILE_BLOCK", "1024")),
+                "hash": 65536}
 BLOCK_TILE_STEP, BLOCK_TILE_MAX = 128, 4096
 BLOCK_ROWS = int(os.environ.get("PFZ_BLOCK_ROWS", "8"))           # from-rows (= warps) per CTA of the block kernel: 8 or 16
 
@@ -388,27 +389,35 @@ class SparseIndex:
         f32 = variant in ("dense32", "block")
         self.post_val32 = torch.empty(cap, dtype=torch.float32, device=dev) if f32 else None
         self.term_maxw = torch.empty(max(self.n_vocab, 1), dtype=torch.float32, device=dev) if variant == "dense32" else None
-        self.post_pk = torch.empty((cap, 2), dtype=torch.int32, device=dev) if variant == "block" else None   # {tile-local row, round(weight * 2^26)}
+        self.post_pk = torch.empty((cap, 2), dtype=torch.int32, device=dev) if variant in ("block", "hash") else None   # {tile-local row, round(weight * 2^26)}
         self.csr = csr                                          # the to-matrix itself (exact re-scoring in dense32 / block)
         ws = _ws((ncell + 1) * 4 + 512 + _lib.load().pfz_scan_ws_bytes(ncell + 1))
         flags = 0
-        if os.environ.get("PFZ_BANK_ORDER", "1") != "0":
+        if os.environ.get("PFZ_BANK_ORDER", "1") != "0" and variant != "hash":
             flags = 2 if f32 else 1                             # 32 four-byte banks for fp32 accumulators, 16 eight-byte banks for fp64
         _lib.call("pfz_index_build", _p(csr.indptr), _p(csr.indices), _p(csr.data), n, self.n_vocab, tile,
                   self.n_tiles, flags, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(self.post_val32), _p(self.term_maxw), _p(ws), _stream())
-        if variant == "block" and n > 0:
+        if variant in ("block", "hash") and n > 0:
             _lib.call("pfz_index_pack_q26", _p(self.post_idx), _p(self.post_val), ctypes.c_void_p(self.seg.data_ptr() + 4 * ncell), _p(self.post_pk), _stream())
 
 
 DENSE32_MAX_ROW_NNZ = 128
 
 
-def choose_variant(density, max_row_nnz=None):
-    """K2 variant for an index: `list` for sparse inputs (density = postings visited per scored pair,
-    NgramTfidf.density(), below DENSE_MIN_DENSITY), else the dense-regime kernel.  The mixed-precision
+HASH_MIN_ROWS = int(os.environ.get("PFZ_HASH_MIN_ROWS", "32768"))   # below this the tile-based list kernel has few tiles to walk
+HASH_MAX_ROW_NNZ = 256
+
+
+def choose_variant(density, max_row_nnz=None, n_to=None):
+    """K2 variant for an index: sparse inputs (density = postings visited per scored pair, NgramTfidf.density(), below
+    DENSE_MIN_DENSITY) take the per-row hash kernel when the to-shard is large (work ~ postings) and the tile-walking
+    `list` kernel otherwise; denser inputs take the dense-regime kernel.  The mixed-precision
     `dense32` filter needs its fp32 error bound (<= ~row_nnz * 2^-24) to stay below half its 2e-5 margin,
     so rows longer than DENSE32_MAX_ROW_NNZ n-grams select the plain fp64 `dense` kernel."""
     if density is None or density < DENSE_MIN_DENSITY:
+        if (density is not None and n_to is not None and n_to >= HASH_MIN_ROWS and max_row_nnz is not None
+                and max_row_nnz <= HASH_MAX_ROW_NNZ and SPARSE_VARIANT == "hash"):
+            return "hash"
         return "list"
     if DENSE_VARIANT in ("dense32", "block") and (max_row_nnz is None or max_row_nnz > DENSE32_MAX_ROW_NNZ):
         return "dense"
@@ -425,7 +434,18 @@ def _auto_splits(n_from, n_tiles, sm_count=148):
 K2_LIST, K2_DENSE, K2_DENSE32 = 1, 2, 3
 DENSE_MIN_DENSITY = float(os.environ.get("PFZ_DENSE_MIN_DENSITY", "0.03"))
 DENSE_VARIANT = os.environ.get("PFZ_DENSE_VARIANT", "block")     # which kernel serves the dense regime
+SPARSE_VARIANT = os.environ.get("PFZ_SPARSE_VARIANT", "hash")    # ... and the sparse regime on large to-shards
 K2_VARIANT = {"list": K2_LIST, "dense": K2_DENSE, "dense32": K2_DENSE32}
+HASH_SLOTS = int(os.environ.get("PFZ_HASH_SLOTS", "0"))          # 0 = choose from the index
+
+
+def _hash_slots(index):
+    """Table size of the hash kernel: ~4x the mean number of postings a from-row visits in this shard."""
+    if HASH_SLOTS:
+        return HASH_SLOTS
+    nnz = index.csr.indices.numel()
+    est = 4.0 * (nnz / max(index.n_vocab, 1)) * (nnz / max(index.n_to, 1))      # 4 x (mean df) x (mean row nnz)
+    return 2048 if est <= 2048 else 8192 if est <= 8192 else 16384
 BLOCK_MAX_ROWS = (1 << 22) - 1                                   # row id field of the block kernel's clustering key
 
 
@@ -475,6 +495,9 @@ def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_mat
             return oi, ov
         variant = "dense32"                                # paging (top_n > 32) runs on the per-row kernel over the same index
     counter = torch.zeros(n_splits, dtype=torch.int32, device=dev)
+    if variant == "hash" and index.post_pk is None:
+        raise ValueError("the index was not built for the hash variant")
+    err = torch.zeros(1, dtype=torch.int32, device=dev) if variant == "hash" else None
     pages = []
     excl_v = excl_i = None
     remaining = k
@@ -484,7 +507,14 @@ def spcos_topk(a: CsrMatrix, index: SparseIndex, k, min_similarity=0.0, self_mat
         tv = torch.empty((n_splits, max(n_from, 1), kp), dtype=torch.float64, device=dev)
         if variant == "dense32" and index.post_val32 is None:
             raise ValueError("the index was not built for the dense32 variant")
-        _lib.call("pfz_spcos_topk", _p(a.indptr), _p(a.indices), _p(a.data), n_from, _p(index.seg), _p(index.post_idx),
+        if variant == "hash":
+            _lib.call("pfz_spcos_topk_hash", _p(a.indptr), _p(a.indices), _p(a.data), n_from, _p(index.seg), _p(index.post_pk),
+                      _p(index.csr.indptr), _p(index.csr.indices), _p(index.csr.data), index.tile, index.n_tiles, index.n_to, kp,
+                      float(min_similarity), int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, _hash_slots(index),
+                      _p(excl_v), _p(excl_i), _p(ti), _p(tv), _p(counter), _p(err), _stream())
+            index._hash_err = err                          # 2 = table overflow, 3 = row > 256 terms (choose_variant rules both out)
+        else:
+          _lib.call("pfz_spcos_topk", _p(a.indptr), _p(a.indices), _p(a.data), n_from, _p(index.seg), _p(index.post_idx),
                   _p(index.post_val), _p(index.post_val32), _p(index.csr.indptr), _p(index.csr.indices), _p(index.csr.data),
                   _p(index.term_maxw), index.n_vocab, index.tile, index.n_tiles, index.n_to, kp, float(min_similarity),
                   int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, _p(excl_v), _p(excl_i),

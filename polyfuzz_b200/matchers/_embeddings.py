@@ -47,6 +47,11 @@ class Embeddings(BaseMatcher):
         top_n = clip_top_n(self.top_n, to_list)
         x, _ = dense.to_bf16_rows(embeddings_from, normalize=True)
         y = x if embeddings_to is embeddings_from else dense.to_bf16_rows(embeddings_to, normalize=True)[0]
-        idx, val = dense.dense_topk(x, y, top_n, self.min_similarity, self_match=to_list is None)
+        # `sparse` thresholds at min_similarity (polyfuzz/models/_utils.py:82); the reference's `sklearn` / `knn` branches
+        # ignore it (_utils.py:59-70, 94-102) and blank scores below 0.001 afterwards: threshold 0 here
+        if self.cosine_method not in ("sparse", "sklearn", "knn"):
+            raise ValueError(f"cosine_method {self.cosine_method!r} unknown (sparse | sklearn | knn)")
+        thr = self.min_similarity if self.cosine_method == "sparse" else 0.0
+        idx, val = dense.dense_topk(x, y, top_n, thr, self_match=to_list is None)
         self.embeddings_to = embeddings_to
         return assemble_matches(from_list, to_list, idx.cpu().numpy(), val.cpu().numpy())

@@ -2,13 +2,11 @@
 vectoriser (K1) and the sparse cosine top-n (K2) on a B200."""
 from typing import List, Tuple
 
-import os
-
 import numpy as np
 import pandas as pd
 
 from ._base import BaseMatcher
-from ._utils import assemble_matches, assemble_matches_chunked, clip_top_n, prepare_strings
+from ._utils import assemble_matches, clip_top_n, prepare_strings
 from .. import engine
 from ..distributed import get_comm, shard_bounds, tfidf_topk_sharded
 from ..strings import ARROW_CACHE
@@ -23,9 +21,12 @@ class TFIDF(BaseMatcher):
         clean_string: Whether to clean the string such that only alphanumerical characters are kept
         min_similarity: The minimum similarity between strings, otherwise return 0 similarity
         top_n: The number of matches you want returned
-        cosine_method: accepted for API compatibility ("sparse" | "sklearn" | "knn"); every value runs
-                       the same fused sparse kernel, which implements the `sparse` branch semantics
-                       (candidates need score > min_similarity, polyfuzz/models/_utils.py:82).
+        cosine_method: "sparse" | "sklearn" | "knn".  Every value runs the same fused GPU kernel; what
+                       differs is the reference branch whose semantics are reproduced: `sparse` keeps
+                       only candidates with score > min_similarity (polyfuzz/models/_utils.py:82), while
+                       the reference's `sklearn` and `knn` branches never look at min_similarity
+                       (_utils.py:59-70, 94-102: every to-string is ranked, scores below 0.001 are blanked
+                       afterwards) -- here: the kernel threshold is 0 for those two methods.
         model_id: The name of the particular instance, used when comparing models
         remove_space_ngrams: Remove n-grams that contain a space
         distributed: (new) when True and torch.distributed is initialised with world size > 1
@@ -73,9 +74,6 @@ class TFIDF(BaseMatcher):
         whole from_list (diagonal excluded) -- one row-block of a self-match that is too large for one
         call / one GPU; the frame has hi-lo rows."""
         ARROW_CACHE.clear()
-        n_chunks = int(os.environ.get("PFZ_MATCH_CHUNKS", "1"))     # experimental (off): overlap scoring with assembly
-        if n_chunks > 1 and from_block is None and not (self.distributed and get_comm() is not None) and len(from_list) >= 20000:
-            return self._match_pipelined(from_list, to_list, re_train, n_chunks)
         top_idx, top_val, top_n = self.match_arrays(from_list, to_list, re_train, from_block)     # kernels are in flight
         rows = from_list if from_block is None else from_list[from_block[0]:from_block[1]]
         targets = to_list if to_list is not None else from_list
@@ -84,35 +82,13 @@ class TFIDF(BaseMatcher):
         ARROW_CACHE.clear()
         return out
 
-    def _match_pipelined(self, from_list, to_list, re_train, n_chunks):
-        """EXPERIMENTAL (PFZ_MATCH_CHUNKS > 1; not validated on hardware in round 1): the from-rows are scored in
-        consecutive blocks; block b's top-k is copied to pinned host memory and assembled while the GPU scores block
-        b+1.  Results are identical to the one-shot path by construction (same kernels per row)."""
-        import torch
-        top_n = clip_top_n(self.top_n, to_list)
-        if top_n < 1:
-            raise ValueError("top_n must be >= 1 and to_list must not be empty")
-        tf_idf_from, _ = self._extract_tf_idf(from_list, to_list, re_train)
-        index = self._safe_index()
-        n = tf_idf_from.n_rows
-        bounds = [(b * n // n_chunks, (b + 1) * n // n_chunks) for b in range(n_chunks)]
-        pending = []
-        for lo, hi in bounds:
-            sub = engine.CsrMatrix(tf_idf_from.indptr[lo:hi + 1], tf_idf_from.indices, tf_idf_from.data, hi - lo, tf_idf_from.n_cols)
-            idx, val = engine.spcos_topk(sub, index, top_n, self.min_similarity, self_match=to_list is None, from_index_base=lo)
-            h_idx = torch.empty(idx.shape, dtype=idx.dtype, pin_memory=True); h_val = torch.empty(val.shape, dtype=val.dtype, pin_memory=True)
-            h_idx.copy_(idx, non_blocking=True); h_val.copy_(val, non_blocking=True)
-            ev = torch.cuda.Event(); ev.record()
-            pending.append((h_idx, h_val, ev))
-        targets = to_list if to_list is not None else from_list
-        prepared = prepare_strings(from_list, targets if to_list is not None else None)
-        chunks = []
-        for h_idx, h_val, ev in pending:
-            ev.synchronize()
-            chunks.append((h_idx.numpy(), h_val.numpy()))
-        out = assemble_matches_chunked(from_list, to_list, chunks, prepared=prepared)
-        ARROW_CACHE.clear()
-        return out
+    def _threshold(self):
+        """Kernel threshold of the reproduced reference branch (see cosine_method in the class docstring)."""
+        if self.cosine_method in ("sklearn", "knn"):
+            return 0.0
+        if self.cosine_method != "sparse":
+            raise ValueError(f"cosine_method {self.cosine_method!r} unknown (sparse | sklearn | knn)")
+        return self.min_similarity
 
     def match_arrays(self, from_list, to_list=None, re_train=True, from_block=None):
         """Device-side result: (top_idx int32[n,k] with -1 for no match, top_val float64[n,k], k)."""
@@ -132,11 +108,11 @@ class TFIDF(BaseMatcher):
             # fit / index on the whole list, score only the block's rows (global diagonal excluded)
             self._extract_tf_idf(from_list, None, re_train)
             block = self.vectorizer.transform(from_list[lo:hi])
-            idx, val = engine.spcos_topk(block, self._safe_index(), top_n, self.min_similarity, self_match=True,
+            idx, val = engine.spcos_topk(block, self._safe_index(), top_n, self._threshold(), self_match=True,
                                          from_index_base=lo)
             return idx, val, top_n
         tf_idf_from, tf_idf_to = self._extract_tf_idf(from_list, to_list, re_train)
-        idx, val = engine.spcos_topk(tf_idf_from, self._safe_index(), top_n, self.min_similarity,
+        idx, val = engine.spcos_topk(tf_idf_from, self._safe_index(), top_n, self._threshold(),
                                      self_match=to_list is None)
         return idx, val, top_n
 
@@ -163,15 +139,17 @@ class TFIDF(BaseMatcher):
                 self._index = None
             tf_idf_from = self._device_to()
         if self._index is None:
-            self._index = engine.SparseIndex(self._device_to(), variant=engine.choose_variant(vec.density(), vec.max_row_nnz))
+            self._index = engine.SparseIndex(self._device_to(), variant=engine.choose_variant(vec.density(), vec.max_row_nnz, self._device_to().n_rows))
         return tf_idf_from, self.tf_idf_to
 
     def _match_sharded(self, comm, from_list, to_list, re_train, top_n, from_block=None):
         if re_train:
             self.vectorizer = engine.NgramTfidf(self.n_gram_range, self.clean_string, self.remove_space_ngrams)
-        elif self.vectorizer is None or self._index is None:
+        elif self.vectorizer is None or self.tf_idf_to is None:
             raise ValueError("re_train=False needs a fitted model (call match/fit first)")
         vec = self.vectorizer
+        if not re_train and self._index is None:             # restored from a pickle: the shard's index is rebuilt from its CSR
+            self._index = engine.SparseIndex(self._device_to(), variant=engine.choose_variant(vec.density(), vec.max_row_nnz, self._device_to().n_rows))
         self_match = to_list is None
         full_to = to_list if to_list else from_list          # `if to_list:` as in _tfidf.py:107
         from_base = 0
@@ -186,11 +164,12 @@ class TFIDF(BaseMatcher):
         else:
             lo, hi = self._shard
             staged_to = None
-        idx, val, csr_to, index = tfidf_topk_sharded(vec, staged_from, staged_to, lo, top_n, self.min_similarity,
+        idx, val, csr_to, index = tfidf_topk_sharded(vec, staged_from, staged_to, lo, top_n, self._threshold(),
                                                      self_match, from_base, fit=re_train, fit_on_from=bool(to_list), comm=comm,
                                                      index=self._index)
         if re_train:
-            self.tf_idf_to, self._index = csr_to, index
+            self.tf_idf_to = csr_to
+        self._index = index                                  # also when a transform had to fall back to the fp64 kernel
         return idx, val
 
     def _safe_index(self):
@@ -198,6 +177,8 @@ class TFIDF(BaseMatcher):
         index for the fp64 kernel then (the to-matrix is unchanged)."""
         if self._index.variant in ("dense32", "block") and self.vectorizer.max_row_nnz > engine.DENSE32_MAX_ROW_NNZ:
             self._index = engine.SparseIndex(self._device_to(), variant="dense")
+        elif self._index.variant == "hash" and self.vectorizer.max_row_nnz > engine.HASH_MAX_ROW_NNZ:
+            self._index = engine.SparseIndex(self._device_to(), variant="list")
         return self._index
 
     def _device_to(self):

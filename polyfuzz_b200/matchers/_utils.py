@@ -62,27 +62,7 @@ def prepare_strings(from_list, to_list):
     return from_pa, to_pa
 
 
-def assemble_matches_chunked(from_list, to_list, chunks, prepared=None) -> pd.DataFrame:
-    """Same frame as assemble_matches, built from consecutive row blocks [(top_idx, top_val), ...] (the pipelined
-    matcher assembles block b while the GPU still scores block b+1)."""
-    parts = [assemble_matches(None, to_list if to_list is not None else from_list, ti, tv, prepared=prepared, _columns_only=True)
-             for ti, tv in chunks]
-    dt = _str_dtype()
-    same = to_list is None or to_list is from_list
-    if dt is None or not parts or parts[0] is None:
-        idx = np.concatenate([c[0] for c in chunks]); val = np.concatenate([c[1] for c in chunks])
-        return assemble_matches(from_list, to_list, idx, val, prepared=prepared)
-    AT = dt.construct_array_type()
-    from_pa = prepared[0] if prepared is not None else prepare_strings(from_list, None if same else to_list)[0]
-    cols = {"From": pd.Series(AT(from_pa, dtype=dt), copy=False)}
-    k = len(parts[0][0])
-    for r in range(k):
-        cols["To" if r == 0 else f"To_{r + 1}"] = pd.Series(AT(pa.chunked_array([p[0][r] for p in parts]), dtype=dt), copy=False)
-        cols["Similarity" if r == 0 else f"Similarity_{r + 1}"] = np.concatenate([p[1][r] for p in parts])
-    return pd.DataFrame(cols, copy=False)
-
-
-def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarray, prepared=None, _columns_only=False):
+def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarray, prepared=None):
     """top_idx int32[n,k] (global to-index, -1 = none), top_val float64[n,k] (unrounded scores).
     Columns From, To, Similarity, To_2, Similarity_2, ... ; similarities rounded to 3 decimals
     (_utils.py:102); Similarity < 0.001 -> 0.0 and To -> None (_utils.py:119-123)."""
@@ -100,26 +80,19 @@ def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarra
     snames = ["Similarity" if r == 0 else f"Similarity_{r + 1}" for r in range(k)]
     dt = _str_dtype()
     cols = {}
-    if _columns_only and (dt is None or n == 0):
-        return None
     if dt is not None and n > 0:
         AT = dt.construct_array_type()
         if prepared is not None:
             from_pa, to_pa = prepared
-        elif _columns_only:
-            from_pa, to_pa = None, pa.array(to_list, type=pa.large_string())
         else:
             from_pa, to_pa = prepare_strings(from_list, None if same else to_list)
-        if not _columns_only:
-            cols["From"] = pd.Series(AT(from_pa, dtype=dt), copy=False)
+        cols["From"] = pd.Series(AT(from_pa, dtype=dt), copy=False)
 
         def gather(r):
             ia = pa.array(idx_t[r], mask=low_t[r])            # masked slots become nulls (their index value is ignored)
             return to_pa.take(ia)
 
         taken = list(_pool().map(gather, range(k))) if (k > 1 and n >= 20000) else [gather(r) for r in range(k)]
-        if _columns_only:
-            return taken, sims_t
         for r in range(k):
             cols[names[r]] = pd.Series(AT(taken[r], dtype=dt), copy=False)
             cols[snames[r]] = sims_t[r]

@@ -82,6 +82,21 @@ def test_c1_match_frames_equal_reference(pf, golden_dir, top_n, ms):
             assert df[c].tolist() == exp
 
 
+@pytest.mark.parametrize("method", ["sklearn", "knn"])
+@pytest.mark.parametrize("top_n", [1, 2, 3])
+def test_c1_sklearn_knn_semantics_ignore_min_similarity(pf, golden_dir, top_n, method):
+    """The reference's sklearn / knn branches never apply min_similarity (polyfuzz/models/_utils.py:59-70, 94-102);
+    the golden ms=0.75 frames were produced by the unmodified reference through its sklearn branch."""
+    polyfuzz_b200, _ = pf
+    ref = json.load(open(os.path.join(golden_dir, "c1_match.json")))
+    m = polyfuzz_b200.TFIDF(min_similarity=0.75, top_n=top_n, cosine_method=method)
+    _frame_eq(m.match(FROM, TO), ref[f"two_top{top_n}_ms0.75"])
+    m = polyfuzz_b200.TFIDF(min_similarity=0.75, top_n=top_n, cosine_method=method)
+    _frame_eq(m.match(FROM), ref[f"self_top{top_n}_ms0.75"])
+    with pytest.raises(ValueError):
+        polyfuzz_b200.TFIDF(cosine_method="annoy").match(FROM, TO)
+
+
 def test_c1_transform_path(pf, golden_dir):
     polyfuzz_b200, _ = pf
     ref = json.load(open(os.path.join(golden_dir, "c1_match.json")))["transform_unseen"]
@@ -299,6 +314,8 @@ def test_dense32_many_exact_ties_and_identical_rows(pf, monkeypatch, variant):
 def test_variant_selection_rules(pf):
     _, engine = pf
     assert engine.choose_variant(0.001, 20) == "list" and engine.choose_variant(None, 20) == "list"
+    assert engine.choose_variant(0.001, 20, 1000) == "list" and engine.choose_variant(0.001, 20, 1_000_000) == "hash"
+    assert engine.choose_variant(0.001, 2000, 1_000_000) == "list"
     assert engine.choose_variant(0.3, 69) == engine.DENSE_VARIANT
     assert engine.choose_variant(0.3, 5000) == "dense" and engine.choose_variant(0.3, None) == "dense"
 
@@ -383,3 +400,25 @@ def test_block_variant_long_rows_split_blocks_and_margin(pf, monkeypatch):
         assert int(ix._block_err.item()) == 0
         np.testing.assert_array_equal(idx.cpu().numpy(), oi)
         np.testing.assert_array_equal(val.cpu().numpy(), ov)
+
+
+@pytest.mark.parametrize("slots", [2048, 8192])
+@pytest.mark.parametrize("k,ms,self_match", [(10, 0.0, False), (3, 0.05, False), (40, 0.0, False), (10, 0.0, True)])
+def test_hash_variant_uniform_strings_vs_oracle(pf, monkeypatch, slots, k, ms, self_match):
+    """The sparse-regime hash kernel (BASELINE config 5 shape at an oracle-sized scale): several 65 536-row tiles, table
+    sizes that force multi-pass rows, paging (top_n > 32), a threshold, and the self-match diagonal."""
+    polyfuzz_b200, engine = pf
+    from polyfuzz_b200 import synth
+    monkeypatch.setattr(engine, "HASH_SLOTS", slots)
+    to = synth.uniform_strings(150_000, seed=0)
+    frm = to[:3000] if self_match else synth.uniform_strings(3000, seed=1) + ["", "zz", to[5], to[70000]]
+    v = engine.NgramTfidf((3, 3), True, True)
+    rows_to, rows_from = v.fit_rows([to, frm])
+    csr_to, csr_from = v.emit(rows_to), v.emit(rows_from)
+    ix = engine.SparseIndex(csr_to, variant="hash")
+    assert ix.tile == 65536 and ix.n_tiles == 3
+    idx, val = engine.spcos_topk(csr_from, ix, k, ms, self_match=self_match)
+    assert int(ix._hash_err.item()) == 0
+    oi, ov = onative.spdot_topn(csr_from.to_scipy(), csr_to.to_scipy(), k, ms, self_match=self_match, n_threads=16)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(val.cpu().numpy(), ov)

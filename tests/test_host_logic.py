@@ -158,16 +158,3 @@ def test_embeddings_matcher_control_flow_with_stubbed_kernels(monkeypatch):
         Embeddings().match(frm, to)                                   # no vectors, no embedder
     emb = Embeddings(embedding_method=lambda strs: rng.normal(size=(len(strs), 8)))
     assert len(emb.match(frm, to)) == 4
-
-
-def test_chunked_assembly_equals_one_shot():
-    from polyfuzz_b200.matchers._utils import assemble_matches_chunked
-    rng = np.random.default_rng(1)
-    frm = [f"f{i}" for i in range(90)]; to = [f"t{i}é" for i in range(40)]
-    idx = rng.integers(-1, 40, (90, 4)).astype(np.int32); val = np.where(idx >= 0, rng.random((90, 4)), 0.0)
-    whole = assemble_matches(frm, to, idx, val)
-    parts = assemble_matches_chunked(frm, to, [(idx[:30], val[:30]), (idx[30:31], val[30:31]), (idx[31:], val[31:])])
-    assert list(parts.columns) == list(whole.columns) and parts.equals(whole)
-    selfw = assemble_matches(frm, None, np.clip(idx, -1, 39), val)
-    selfp = assemble_matches_chunked(frm, None, [(np.clip(idx, -1, 39)[:50], val[:50]), (np.clip(idx, -1, 39)[50:], val[50:])])
-    assert selfp.equals(selfw)
