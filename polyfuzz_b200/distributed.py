@@ -59,6 +59,44 @@ class Comm:
         return unpack_topk(out.view((self.world_size, n) + tuple(local.shape[1:])))
 
 
+    def all_gather_best(self, idx, score, dist_):
+        """Per-shard best matches (int32 idx[n] GLOBAL or -1, float64 score[n], int32 dist[n]) of every rank
+        -> ([G,n], [G,n], [G,n]); ONE collective (the edit-distance matchers' exchange)."""
+        n = idx.shape[0]
+        local = torch.empty((n, 2), dtype=torch.int64, device=idx.device)
+        local[:, 0] = score.contiguous().view(torch.int64)
+        local[:, 1] = (idx.to(torch.int64) & 0xffffffff) | (dist_.to(torch.int64) << 32)
+        out = torch.empty((self.world_size * n, 2), dtype=torch.int64, device=idx.device)
+        dist.all_gather_into_tensor(out, local, group=self.group)
+        out = out.view(self.world_size, n, 2)
+        sc = out[..., 0].contiguous().view(torch.float64)
+        lo32 = out[..., 1] & 0xffffffff
+        gi = torch.where(lo32 >= 2 ** 31, lo32 - 2 ** 32, lo32).to(torch.int32).contiguous()
+        gd = (out[..., 1] >> 32).to(torch.int32).contiguous()
+        return gi, sc, gd
+
+
+def merge_topk_any(idx, val, k_out):
+    """Canonical merge of [G, n, k_in] per-shard lists into [n, k_out]: the pfz_topk_merge kernel up to 32, and for larger
+    top_n two stable device sorts by the same key (score desc, index asc; empty slots last)."""
+    from . import engine
+    if k_out <= 32:
+        return engine.topk_merge(idx, val, k_out)
+    G, n, k_in = idx.shape
+    ci = idx.permute(1, 0, 2).reshape(n, G * k_in)
+    cv = val.permute(1, 0, 2).reshape(n, G * k_in)
+    empty = ci < 0
+    key_i = torch.where(empty, torch.full_like(ci, 2 ** 31 - 1), ci)
+    o1 = torch.argsort(key_i, dim=1, stable=True)
+    ci1, cv1, e1 = torch.gather(ci, 1, o1), torch.gather(cv, 1, o1), torch.gather(empty, 1, o1)
+    key_v = torch.where(e1, torch.full_like(cv1, float("-inf")), cv1)
+    o2 = torch.argsort(key_v, dim=1, descending=True, stable=True)
+    oi = torch.gather(ci1, 1, o2)[:, :k_out].contiguous()
+    ov = torch.gather(cv1, 1, o2)[:, :k_out].contiguous()
+    ov = torch.where(oi < 0, torch.zeros_like(ov), ov)
+    return oi, ov
+
+
 def get_comm(group=None):
     """Comm for the default group, or None when not running distributed (world size 1)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -72,8 +110,6 @@ def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, 
     """Sharded TF-IDF top-k.  Every rank passes the same from-list and its own to-shard.
     Returns (top_idx[n_from,k] GLOBAL indices, top_val[n_from,k], csr_to_shard, index)."""
     from . import engine
-    if top_n > 32 and comm is not None:
-        raise NotImplementedError("multi-GPU top_n > 32 is not supported yet")
     ev1 = None
     if k1_timings is not None:                              # K1 + index build, for bench.py's per-kernel breakdown
         ev1 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -110,6 +146,6 @@ def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, 
         ev[1].record()
         timings.append(ev)
     if comm is not None:
-        gi, gv = comm.all_gather_topk(idx, val)
-        idx, val = engine.topk_merge(gi, gv, top_n)
+        gi, gv = comm.all_gather_topk(idx.contiguous(), val.contiguous())
+        idx, val = merge_topk_any(gi, gv, top_n)
     return idx, val, csr_to, index

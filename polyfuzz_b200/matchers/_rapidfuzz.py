@@ -18,6 +18,22 @@ import pandas as pd
 
 from ._base import BaseMatcher
 from .. import editdist
+from ..distributed import get_comm, shard_bounds
+
+
+def _argbest(from_list, targets, metric, cutoff, self_match, distributed):
+    """Best to-string per from-string on this GPU, or -- distributed=True under torchrun -- on the to_list row-block of every
+    rank followed by ONE all-gather of the per-shard bests and the canonical merge (score desc, global index asc): all ranks
+    get the single-GPU result (the reference's own fan-out is per from-row, polyfuzz/models/_rapidfuzz.py:92-95)."""
+    comm = get_comm() if distributed else None
+    if comm is None:
+        return editdist.edit_argbest(from_list, targets, metric, cutoff, exclude_self=self_match)
+    lo, hi = shard_bounds(len(targets), comm.world_size, comm.rank)
+    Q = editdist.EditQueries(from_list)
+    T = editdist.EditTargets(targets[lo:hi])
+    bi, bs, bd = editdist.edit_argbest_staged(Q, T, metric, cutoff, exclude_self=self_match, self_shift=-lo, to_index_base=lo)
+    gi, gs, gd = comm.all_gather_best(bi, bs, bd)
+    return editdist.lev_merge(gi, gs, gd)
 
 _NAMES = {"ratio": "ratio", "levenshtein": "norm_lev", "norm_lev": "norm_lev", "normalized_similarity": "norm_lev",
           "normalized_levenshtein": "norm_lev"}
@@ -41,9 +57,11 @@ class RapidFuzz(BaseMatcher):
     scores all pairs in one launch), score_cutoff in [0,1], scorer (default "ratio"; the reference
     defaults to fuzz.WRatio, which is not on the GPU path), model_id."""
 
-    def __init__(self, n_jobs: int = 1, score_cutoff: float = 0, scorer: Union[str, Callable] = "ratio", model_id: str = None):
+    def __init__(self, n_jobs: int = 1, score_cutoff: float = 0, scorer: Union[str, Callable] = "ratio", model_id: str = None,
+                 distributed: bool = False):
         super().__init__(model_id)
         self.type = "EditDistance"
+        self.distributed = distributed
         self.score_cutoff = score_cutoff * 100
         self.scorer = scorer
         self._metric = _resolve_scorer(scorer)
@@ -57,7 +75,7 @@ class RapidFuzz(BaseMatcher):
         targets = from_list if self_match else to_list
         scale = 100.0 if self._metric == "ratio" else 1.0
         cutoff = self.score_cutoff if self._metric == "ratio" else self.score_cutoff / 100.0
-        idx, score, _ = editdist.edit_argbest(from_list, targets, self._metric, cutoff, exclude_self=self_match)
+        idx, score, _ = _argbest(from_list, targets, self._metric, cutoff, self_match, self.distributed)
         idx = idx.cpu().numpy(); score = score.cpu().numpy() / scale
         to_arr = np.empty(len(targets) + 1, dtype=object); to_arr[:-1] = targets; to_arr[-1] = None
         sel = np.where(idx >= 0, idx, len(targets))
@@ -70,9 +88,11 @@ class EditDistance(BaseMatcher):
     Similarity is the scorer's raw value (fuzz.ratio: 0..100) of the best to-string, min-max normalised
     over the column when `normalize` (polyfuzz/models/_distance.py:83-86)."""
 
-    def __init__(self, n_jobs: int = 1, scorer: Union[str, Callable] = "ratio", model_id: str = None, normalize: bool = True):
+    def __init__(self, n_jobs: int = 1, scorer: Union[str, Callable] = "ratio", model_id: str = None, normalize: bool = True,
+                 distributed: bool = False):
         super().__init__(model_id)
         self.type = "EditDistance"
+        self.distributed = distributed
         self.scorer = scorer
         self._metric = _resolve_scorer(scorer)
         self.normalize = normalize
@@ -84,7 +104,7 @@ class EditDistance(BaseMatcher):
         targets = from_list if self_match else to_list
         if len(targets) - (1 if self_match else 0) < 1:
             raise ValueError("attempt to get argmax of an empty sequence")         # np.argmax on [] in the reference
-        idx, score, _ = editdist.edit_argbest(from_list, targets, self._metric, float("-inf"), exclude_self=self_match)
+        idx, score, _ = _argbest(from_list, targets, self._metric, float("-inf"), self_match, self.distributed)
         idx = idx.cpu().numpy(); score = score.cpu().numpy()
         to_arr = np.empty(len(targets), dtype=object); to_arr[:] = targets
         matches = pd.DataFrame({"From": pd.Series(list(from_list), dtype=object), "To": pd.Series(to_arr[idx], dtype=object),

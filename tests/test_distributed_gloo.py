@@ -36,6 +36,26 @@ def _worker(rank, world, port, out):
         mi, mv = native.topk_merge(gi.numpy(), gv.numpy(), 5)
         fi, fv = native.spdot_topn(f, t, 5, 0.0)
         assert np.array_equal(mi, fi) and np.array_equal(mv, fv)
+        # top_n > 32: the sort-based canonical merge (same key) against the oracle's merge
+        from polyfuzz_b200.distributed import merge_topk_any
+        li, lv = native.spdot_topn(f, t[lo:hi], 40, 0.0, to_index_base=lo)
+        gi, gv = comm.all_gather_topk(torch.from_numpy(li), torch.from_numpy(lv))
+        mi2, mv2 = merge_topk_any(gi, gv, 40)
+        fi, fv = native.spdot_topn(f, t, 40, 0.0)
+        assert np.array_equal(mi2.numpy(), fi) and np.array_equal(mv2.numpy(), fv)
+        # edit-distance exchange: per-shard best (global index, score, distance) -> one all-gather -> first maximum
+        bi, bs, bd = native.editdist_argbest(frm[:40], to[lo:hi], "ratio")
+        bi = np.where(bi >= 0, bi + lo, bi).astype(np.int32)
+        gi, gs, gd = comm.all_gather_best(torch.from_numpy(bi), torch.from_numpy(bs), torch.from_numpy(bd))
+        assert gi.shape == (world, 40) and gi.dtype == torch.int32 and gs.dtype == torch.float64 and gd.dtype == torch.int32
+        ref_i, ref_s, ref_d = native.editdist_argbest(frm[:40], to, "ratio")
+        best = np.full(40, -1, np.int32); bsc = np.zeros(40); bdd = np.full(40, -1, np.int32)
+        for r in range(world):
+            for q in range(40):
+                j, sc = int(gi[r, q]), float(gs[r, q])
+                if j >= 0 and (best[q] < 0 or sc > bsc[q] or (sc == bsc[q] and j < best[q])):
+                    best[q], bsc[q], bdd[q] = j, sc, int(gd[r, q])
+        assert np.array_equal(best, ref_i) and np.array_equal(bsc, ref_s) and np.array_equal(bdd, ref_d)
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))
