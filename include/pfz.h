@@ -263,6 +263,21 @@ int pfz_dense_cos_topk(const void *x_bf16, const void *y_bf16, int32_t n_from, i
                        double min_similarity, int32_t self_match, int64_t from_index_base, int64_t to_index_base,
                        int32_t n_splits, int32_t *top_idx, double *top_val, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K5  frame tail: top-k arrays -> the columns of the result frame (csrc/pfz_assemble.cu).
+ * Replaces: polyfuzz/models/_utils.py:104-125 (the per-rank `[to_list[idx] ...]` gathers, the 3-decimal rounding of :102/:143
+ *           and the `Similarity < 0.001 -> 0, To -> None` rule of :119-123).  ASCII string lists only (bytes == code points).
+ * Column-major entries e = r*n + i (r = rank 0..k-1, i = from-row):
+ *   sims    float64[k*n]     np.round(score, 3), 0 where the slot is empty or rounds below 0.001
+ *   lens_pos int32[k*n + 1]  on return the EXCLUSIVE prefix of the matched strings' byte lengths (last entry = total bytes)
+ *   bitmap  uint32[k * ceil(n/32)]   Arrow validity bits (bit i of column r)
+ *   ws: >= pfz_scan_ws_bytes(k*n + 1) bytes.
+ * then, with the total known to the caller: offsets int32[k*(n+1)] (relative to each column's start) and the UTF-8 bytes.   */
+int pfz_frame_tail_count(const int32_t *top_idx, const double *top_val, int32_t n, int32_t k, const int64_t *to_offsets, double *sims,
+                         int32_t *lens_pos, uint32_t *bitmap, void *ws, void *stream);
+int pfz_frame_tail_copy(const int32_t *top_idx, int32_t n, int32_t k, const int32_t *to_blob, const int64_t *to_offsets, const int32_t *pos,
+                        int32_t *offsets, uint8_t *data, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,36 @@ def merge_topk_any(idx, val, k_out):
     return oi, ov
 
 
+def gather_string_shards(comm, S):
+    """All-gather the ranks' device-resident to-list shards (engine.StagedStrings) into the whole list on every rank:
+    -> (blob int32[n_chars_total], offsets int64[n_total + 1], all_ascii, None).  Two small collectives (sizes, then the padded
+    byte blobs + offsets); used by the device frame tail (K5) so that no rank has to pack the other ranks' strings."""
+    dev = S.d_off.device
+    meta = torch.tensor([S.n_chars, S.n, int(bool(S.ascii))], dtype=torch.int64, device=dev)
+    metas = torch.empty((comm.world_size, 3), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(metas.view(-1), meta, group=comm.group)
+    metas = metas.cpu()
+    if int(metas[:, 2].min()) == 0:
+        return (None, None, False, None)
+    max_c, max_n = int(metas[:, 0].max()), int(metas[:, 1].max())
+    loc_b = torch.zeros(max(max_c, 1), dtype=torch.uint8, device=dev)
+    loc_b[:S.n_chars] = S.d_blob[:S.n_chars].to(torch.uint8)
+    loc_o = torch.zeros(max_n + 1, dtype=torch.int64, device=dev)
+    loc_o[:S.n + 1] = S.d_off[:S.n + 1]
+    all_b = torch.empty((comm.world_size, loc_b.numel()), dtype=torch.uint8, device=dev)
+    all_o = torch.empty((comm.world_size, max_n + 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_b.view(-1), loc_b, group=comm.group)
+    dist.all_gather_into_tensor(all_o.view(-1), loc_o, group=comm.group)
+    blobs, offs, base = [], [], 0
+    for r in range(comm.world_size):
+        nc, nr = int(metas[r, 0]), int(metas[r, 1])
+        blobs.append(all_b[r, :nc].to(torch.int32))
+        offs.append(all_o[r, :nr] + base)
+        base += nc
+    offs.append(torch.tensor([base], dtype=torch.int64, device=dev))
+    return (torch.cat(blobs) if base else torch.zeros(1, dtype=torch.int32, device=dev), torch.cat(offs), True, None)
+
+
 def get_comm(group=None):
     """Comm for the default group, or None when not running distributed (world size 1)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

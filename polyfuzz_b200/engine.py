@@ -112,7 +112,8 @@ class CsrMatrix:
 
 class StagedStrings:
     """One string list packed and resident in HBM (UTF-32 blob, offsets, n-gram slot prefix)."""
-    __slots__ = ("n", "n_chars", "d_blob", "d_off", "occ_ptr", "d_long", "n_long", "cap", "h2d_bytes", "lo", "hi", "max_slots")
+    __slots__ = ("n", "n_chars", "d_blob", "d_off", "occ_ptr", "d_long", "n_long", "cap", "h2d_bytes", "lo", "hi", "max_slots",
+                 "ascii", "host_blob", "host_off")
 
 
 def stage_strings(strings, lo, hi):
@@ -127,6 +128,8 @@ def stage_strings(strings, lo, hi):
     S = StagedStrings()
     S.n, S.n_chars, S.cap, S.lo, S.hi = len(strings), int(blob.size), int(occ[-1]), lo, hi
     S.max_slots = int(slots.max()) if len(slots) else 0        # upper bound of any row's nnz
+    S.ascii = blob.dtype == np.uint8                           # bytes == code points: the frame tail can run on the device (K5)
+    S.host_blob, S.host_off = (blob, offsets) if S.ascii else (None, None)
     if blob.size == 0:
         S.d_blob = torch.zeros(1, dtype=torch.int32, device=_dev())
     elif blob.dtype == np.uint8:                              # ASCII list: 1 byte per code point over PCIe, widened in HBM

@@ -6,9 +6,10 @@ import numpy as np
 import pandas as pd
 
 from ._base import BaseMatcher
-from ._utils import assemble_matches, clip_top_n, prepare_strings
+from ._utils import (arrow_from_staged, assemble_matches, assemble_matches_device, clip_top_n, device_tail_available,
+                     prepare_strings)
 from .. import engine
-from ..distributed import get_comm, shard_bounds, tfidf_topk_sharded
+from ..distributed import gather_string_shards, get_comm, shard_bounds, tfidf_topk_sharded
 from ..strings import ARROW_CACHE
 
 
@@ -57,10 +58,13 @@ class TFIDF(BaseMatcher):
         self.distributed = distributed
         self._index = None              # device inverted index of tf_idf_to (rebuilt lazily after unpickling)
         self._shard = (0, 0)            # distributed: [lo, hi) to-rows owned by this rank
+        self._st_to = None              # device-resident to-list (blob, offsets) for the frame tail; not pickled
+        self._st_from = None            # ... and the from-rows of the current call
 
     def __getstate__(self):
         st = dict(self.__dict__)
         st["_index"] = None
+        st["_st_to"] = st["_st_from"] = None
         if self.tf_idf_to is not None and not hasattr(self.tf_idf_to, "tocsr"):
             st["tf_idf_to"] = self.tf_idf_to.to_scipy()          # device CSR -> host scipy for joblib.dump
         return st
@@ -74,7 +78,13 @@ class TFIDF(BaseMatcher):
         whole from_list (diagonal excluded) -- one row-block of a self-match that is too large for one
         call / one GPU; the frame has hi-lo rows."""
         ARROW_CACHE.clear()
+        self._st_from = None
         top_idx, top_val, top_n = self.match_arrays(from_list, to_list, re_train, from_block)     # kernels are in flight
+        st_from, st_to = self._st_from, self._st_to
+        self._st_from = None
+        if top_idx.shape[0] > 0 and st_to is not None and device_tail_available(st_from) and st_to[2]:
+            # K5: rounding, blanking and the per-rank string gathers on the device; the host wraps the finished columns
+            return assemble_matches_device(arrow_from_staged(st_from), st_to[0], st_to[1], top_idx, top_val)
         rows = from_list if from_block is None else from_list[from_block[0]:from_block[1]]
         targets = to_list if to_list is not None else from_list
         prepared = prepare_strings(rows, targets if (to_list is not None or from_block is not None) else None)   # overlaps the GPU
@@ -107,7 +117,9 @@ class TFIDF(BaseMatcher):
         if from_block is not None:
             # fit / index on the whole list, score only the block's rows (global diagonal excluded)
             self._extract_tf_idf(from_list, None, re_train)
-            block = self.vectorizer.transform(from_list[lo:hi])
+            block_rows = self.vectorizer.rows(from_list[lo:hi])
+            self._st_from = block_rows._keep
+            block = self.vectorizer.emit(block_rows)
             idx, val = engine.spcos_topk(block, self._safe_index(), top_n, self._threshold(), self_match=True,
                                          from_index_base=lo)
             return idx, val, top_n
@@ -129,18 +141,29 @@ class TFIDF(BaseMatcher):
                 rows_to, rows_from = vec.fit_rows([to_list, from_list])
                 self.tf_idf_to = vec.emit(rows_to)
                 self._index = None
+                self._st_to = self._tail_of(rows_to._keep)
             else:
                 rows_from = vec.rows(from_list)
+            self._st_from = rows_from._keep
             tf_idf_from = vec.emit(rows_from)
         else:
             if re_train:
                 (rows_from,) = vec.fit_rows([from_list])
                 self.tf_idf_to = vec.emit(rows_from)
                 self._index = None
+                self._st_to = self._tail_of(rows_from._keep)
+                self._st_from = rows_from._keep
+            elif self._st_to is not None:
+                self._st_from = self._st_to[3]
             tf_idf_from = self._device_to()
         if self._index is None:
             self._index = engine.SparseIndex(self._device_to(), variant=engine.choose_variant(vec.density(), vec.max_row_nnz, self._device_to().n_rows))
         return tf_idf_from, self.tf_idf_to
+
+    @staticmethod
+    def _tail_of(S):
+        """(device blob int32, device offsets int64, ascii?, staged list) of a to-list kept for the frame tail (K5)."""
+        return (S.d_blob, S.d_off, bool(S.ascii), S)
 
     def _match_sharded(self, comm, from_list, to_list, re_train, top_n, from_block=None):
         if re_train:
@@ -157,10 +180,14 @@ class TFIDF(BaseMatcher):
             from_base = int(from_block[0])
             from_list = from_list[from_block[0]:from_block[1]]
         staged_from = vec.stage(from_list)
+        self._st_from = staged_from
         if re_train:
             lo, hi = shard_bounds(len(full_to), comm.world_size, comm.rank)
             self._shard = (lo, hi)
             staged_to = vec.stage(full_to[lo:hi])
+            # the frame tail needs every to-string on every rank: the shards' blobs are all-gathered over NCCL (bytes), so the
+            # host work per rank stays that of its own shard
+            self._st_to = gather_string_shards(comm, staged_to)
         else:
             lo, hi = self._shard
             staged_to = None

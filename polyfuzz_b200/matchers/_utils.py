@@ -107,3 +107,57 @@ def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarra
         cols[names[r]] = pd.Series(to_arr[idx], dtype=object)
         cols[snames[r]] = sims_t[r]
     return pd.DataFrame(cols)
+
+
+def device_tail_available(*staged):
+    """The frame tail can run on the device (K5) when every list involved is ASCII and pandas has its Arrow-backed str dtype."""
+    return _str_dtype() is not None and all(s is not None and getattr(s, "ascii", False) for s in staged)
+
+
+def arrow_from_staged(S, lo=0, hi=None):
+    """Zero-copy Arrow view of an ASCII string list packed by the host (blob bytes + int64 offsets)."""
+    n = S.n if hi is None else hi
+    arr = pa.LargeStringArray.from_buffers(S.n, pa.py_buffer(S.host_off), pa.py_buffer(S.host_blob))
+    return arr if (lo == 0 and n == S.n) else arr.slice(lo, n - lo)
+
+
+def assemble_matches_device(from_arrow, to_blob, to_off, top_idx, top_val) -> pd.DataFrame:
+    """K5: the frame tail of polyfuzz/models/_utils.py:104-125 on the device.  top_idx / top_val are the DEVICE top-k arrays,
+    to_blob / to_off the device-resident to-list (int32 code points of an ASCII list, int64 offsets).  Rounding, the
+    `< 0.001 -> None` rule and the per-rank string gathers run in two kernels; one D2H brings the finished columns back and
+    Arrow / pandas wrap them without copying."""
+    import ctypes
+    import torch
+    from .. import _lib
+    from ..engine import _p, _stream, _ws
+    n, k = top_idx.shape
+    dev = top_idx.device
+    dt = _str_dtype()
+    AT = dt.construct_array_type()
+    nw = (n + 31) // 32
+    top_idx = top_idx.contiguous(); top_val = top_val.contiguous()
+    sims = torch.empty(k * n, dtype=torch.float64, device=dev)
+    pos = torch.empty(k * n + 1, dtype=torch.int32, device=dev)
+    bitmap = torch.empty(k * nw, dtype=torch.int32, device=dev)
+    ws = _ws(_lib.load().pfz_scan_ws_bytes(k * n + 1))
+    _lib.call("pfz_frame_tail_count", _p(top_idx), _p(top_val), n, k, _p(to_off), _p(sims), _p(pos), _p(bitmap), _p(ws), _stream())
+    total = int(pos[-1].item())                               # the one host sync of the tail (everything before it is done by then)
+    offsets = torch.empty(k * (n + 1), dtype=torch.int32, device=dev)
+    data = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    _lib.call("pfz_frame_tail_copy", _p(top_idx), n, k, _p(to_blob), _p(to_off), _p(pos), _p(offsets), _p(data), _stream())
+    # one buffer, one D2H: [sims | offsets | bitmap | data]
+    parts = [sims.view(torch.uint8), offsets.view(torch.uint8), bitmap.view(torch.uint8), data[:total]]
+    sizes = [p.numel() for p in parts]
+    host = torch.cat(parts).cpu().numpy()
+    o = np.cumsum([0] + sizes)
+    h_sims = host[o[0]:o[1]].view(np.float64).reshape(k, n)
+    h_off = host[o[1]:o[2]].view(np.int32).reshape(k, n + 1)
+    h_bm = host[o[2]:o[3]].reshape(k, nw * 4)
+    h_data = host[o[3]:o[4]]
+    col0 = np.concatenate([[0], np.cumsum(h_off[:, n].astype(np.int64))])     # byte range of every column in `data`
+    cols = {"From": pd.Series(AT(from_arrow, dtype=dt), copy=False)}
+    for r in range(k):
+        arr = pa.StringArray.from_buffers(n, pa.py_buffer(h_off[r]), pa.py_buffer(h_data[col0[r]:col0[r + 1]]), pa.py_buffer(h_bm[r]))
+        cols["To" if r == 0 else f"To_{r + 1}"] = pd.Series(AT(arr, dtype=dt), copy=False)
+        cols["Similarity" if r == 0 else f"Similarity_{r + 1}"] = h_sims[r]
+    return pd.DataFrame(cols, copy=False)

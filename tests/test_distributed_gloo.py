@@ -56,6 +56,17 @@ def _worker(rank, world, port, out):
                 if j >= 0 and (best[q] < 0 or sc > bsc[q] or (sc == bsc[q] and j < best[q])):
                     best[q], bsc[q], bdd[q] = j, sc, int(gd[r, q])
         assert np.array_equal(best, ref_i) and np.array_equal(bsc, ref_s) and np.array_equal(bdd, ref_d)
+        # frame-tail exchange: the ranks' string shards (bytes + offsets) -> the whole list on every rank
+        from types import SimpleNamespace
+        from polyfuzz_b200.distributed import gather_string_shards
+        mine = to[lo:hi]
+        blob = np.frombuffer("".join(mine).encode("ascii"), dtype=np.uint8).astype(np.int32)
+        offs = np.zeros(len(mine) + 1, dtype=np.int64); np.cumsum([len(x) for x in mine], out=offs[1:])
+        S = SimpleNamespace(n=len(mine), n_chars=int(blob.size), ascii=True, d_blob=torch.from_numpy(blob), d_off=torch.from_numpy(offs))
+        gb, go, ok_ascii, _ = gather_string_shards(comm, S)
+        assert ok_ascii and go.numel() == len(to) + 1
+        whole = bytes(gb.to(torch.uint8).numpy()).decode("ascii")
+        assert [whole[int(go[i]):int(go[i + 1])] for i in range(len(to))] == to
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))

@@ -158,3 +158,16 @@ def test_embeddings_matcher_control_flow_with_stubbed_kernels(monkeypatch):
         Embeddings().match(frm, to)                                   # no vectors, no embedder
     emb = Embeddings(embedding_method=lambda strs: rng.normal(size=(len(strs), 8)))
     assert len(emb.match(frm, to)) == 4
+
+
+def test_arrow_view_of_a_staged_ascii_list():
+    """The From column of the device frame tail is a zero-copy Arrow view of the host packer's bytes + offsets."""
+    from types import SimpleNamespace
+    from polyfuzz_b200.matchers._utils import arrow_from_staged, device_tail_available
+    from polyfuzz_b200.strings import pack_strings
+    lst = ["alpha", "", "b c", "Zeta-9"]
+    blob, off, _ = pack_strings(lst)
+    assert blob.dtype == np.uint8
+    S = SimpleNamespace(n=len(lst), ascii=True, host_blob=blob, host_off=off)
+    assert arrow_from_staged(S).to_pylist() == lst and arrow_from_staged(S, 1, 3).to_pylist() == lst[1:3]
+    assert device_tail_available(S) and not device_tail_available(S, None) and not device_tail_available(SimpleNamespace(ascii=False))
