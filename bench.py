@@ -561,11 +561,14 @@ def run_b200(args):
                         "is the same time against the reference's fp64 byte count (s = 8).  The index (~8-16 MB) is L2-resident: DRAM "
                         "traffic << algorithmic bytes by design (SURVEY 8d)"}
 
-    h2d = staged_from.h2d_bytes * (1 if world == 1 else 2) + vec.n_vocab * 8
-    d2h = n * TOP_N * 12 + vec.n_vocab * 12 + 4
+    from polyfuzz_b200.matchers._utils import LAST_TAIL
+    h2d = staged_from.h2d_bytes * (1 if world == 1 else 2) + (n + 1) * 8            # packed strings + offsets + slot prefix, idf table
+    d2h = LAST_TAIL["d2h_bytes"] + 3 * 8                                            # finished frame columns (K5) + the fit's three scalars
     e2e = {"value": pairs / (e2e_ms_per_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": e2e_ms_per_step, "steps": len(e2e_ms), "ms_each": [round(x, 2) for x in e2e_ms],
-           "what": "TFIDF.match(list[str]) -> pandas.DataFrame: UTF-32 packing, H2D, K1, index, K2, D2H, frame assembly"}
+           "frame_tail": "device (K5)" if LAST_TAIL["device"] else "host (Arrow)",
+           "what": "TFIDF.match(list[str]) -> pandas.DataFrame: string packing, H2D, K1, index, K2, frame tail (rounding + string gathers"
+                   " on the device), D2H of the finished columns, zero-copy Arrow/pandas wrap"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

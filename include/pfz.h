@@ -94,6 +94,11 @@ int pfz_sort_u64(uint64_t *keys, int64_t n_pow2, void *stream);
 int pfz_vocab_from_sorted(const uint64_t *sorted_keys, int64_t n_keys_cap, const int64_t *n_keys_dev,
                           uint64_t *vocab_keys, int32_t *df, int32_t *n_vocab_dev, void *ws, void *stream);
 
+/* idf[v] = table[df[v]] for v < *n_vocab_dev: the host evaluates sklearn's np.log((n+1)/(df+1)) + 1 (sk:feature_extraction/text.py:
+ * 1679-1694) once for every possible df = 0..n_docs with numpy (same bits as the reference) and the device only looks it up, so
+ * neither df nor idf crosses PCIe during a fit.                                                                              */
+int pfz_idf_lookup(const int32_t *df, const int32_t *n_vocab_dev, int64_t cap, const double *table, int64_t n_table, double *idf, void *stream);
+
 /* Stage C: emit the l2-normalised TF-IDF CSR for one list with a FIXED vocabulary (transform).
  *   lookup: rank_dense (may be NULL) else binary search in vocab_keys[n_vocab]; OOV n-grams dropped
  *   idf: float64[n_vocab] (computed by the host with numpy exactly as sklearn does, text.py:1679-1694)

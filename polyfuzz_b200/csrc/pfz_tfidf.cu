@@ -257,6 +257,16 @@ __global__ void __launch_bounds__(256) gather_codes_kernel(const uint64_t *__res
     }
 }
 
+// idf[v] = table[df[v]] for v < *n_vocab (the table holds sklearn's idf for every possible df, computed by numpy on the host)
+__global__ void idf_lookup_kernel(const int32_t *__restrict__ df, const int32_t *__restrict__ n_vocab, int64_t cap, const double *__restrict__ table,
+                                  int64_t n_table, double *__restrict__ idf) {
+    const int64_t nv = min((int64_t)*n_vocab, cap);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = df[i];
+        idf[i] = table[d < n_table ? d : n_table - 1];
+    }
+}
+
 // global bitonic sort of uint64 keys (n power of two)
 constexpr int BS_TILE = 4096;      // keys per block for the shared-memory stages (32 KB)
 constexpr int BS_THREADS = 512;
@@ -470,6 +480,14 @@ int pfz_gather_codes(const uint64_t *codes, const int64_t *occ_ptr, const int32_
     if (n_rows <= 0) return 0;
     gather_codes_kernel<<<grid_for((int64_t)n_rows * 32, 256), 256, 0, as_stream(stream)>>>(codes, occ_ptr, row_cnt, n_rows, keys,
                                                                                              reinterpret_cast<unsigned long long *>(cursor_dev));
+    PFZ_LAUNCH_OK();
+    return 0;
+}
+
+int pfz_idf_lookup(const int32_t *df, const int32_t *n_vocab_dev, int64_t cap, const double *table, int64_t n_table, double *idf, void *stream) {
+    if (cap <= 0) return 0;
+    PFZ_REQUIRE(n_table >= 1, "pfz_idf_lookup: empty table");
+    idf_lookup_kernel<<<grid_for(cap, 256), 256, 0, as_stream(stream)>>>(df, n_vocab_dev, cap, table, n_table, idf);
     PFZ_LAUNCH_OK();
     return 0;
 }

@@ -144,6 +144,21 @@ def stage_strings(strings, lo, hi):
     return S
 
 
+_IDF_TABLES = {}
+
+
+def _idf_table(n_docs):
+    """Device table idf(df) for df = 0..n_docs with scikit-learn's expression evaluated by numpy on the host (cached per n_docs)."""
+    key = (int(n_docs), torch.cuda.current_device())
+    t = _IDF_TABLES.get(key)
+    if t is None:
+        tab = np.log((n_docs + 1.0) / (np.arange(0, n_docs + 1, dtype=np.float64) + 1.0)) + 1.0
+        if len(_IDF_TABLES) > 8:
+            _IDF_TABLES.clear()
+        t = _IDF_TABLES[key] = _to_dev(tab)
+    return t
+
+
 class _Rows:
     """Stage-A result for one string list: per-row sorted distinct n-gram codes + counts."""
     __slots__ = ("n", "occ_ptr", "codes", "tf", "row_cnt", "cap", "_keep")
@@ -164,23 +179,50 @@ class NgramTfidf:
         self.flags = (FLAG_CLEAN if self.clean else 0) | (FLAG_REMOVE_SPACE if self.remove_space else 0)
         self.base = CLEAN_BASE if self.clean else None
         self.alphabet = None            # raw mode: sorted code points of the fit corpus (numpy uint32)
-        self.vocab_keys = None          # numpy uint64[V] ascending (host copy, for pickling / inspection)
-        self.idf = None                 # numpy float64[V]
-        self.df = None
+        self._h_vocab_keys = None       # numpy uint64[V] ascending (host copies are made lazily: pickling / inspection)
+        self._h_idf = None              # numpy float64[V]
+        self._h_df = None
+        self._n_vocab = 0
+        self._sum_df_sq = None          # sum_t df_t^2 (density of the fitted corpus), from the fit's one small D2H
         self.n_fit_docs = 0
         self.max_row_nnz = 0            # upper bound over every list seen (fit and transform)
-        self._d_sym = self._d_vocab = self._d_idf = self._d_rank = None
+        self._d_sym = self._d_vocab = self._d_idf = self._d_rank = self._d_df = None
 
     # ---- pickling: device tensors are rebuilt lazily ---------------------------------------------
     def __getstate__(self):
+        if self._n_vocab:
+            self.vocab_keys, self.df, self.idf                  # materialise the host copies
         st = dict(self.__dict__)
-        for k in ("_d_sym", "_d_vocab", "_d_idf", "_d_rank"):
+        for k in ("_d_sym", "_d_vocab", "_d_idf", "_d_rank", "_d_df"):
             st[k] = None
         return st
 
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self.__dict__.setdefault("_d_df", None)
+
     @property
     def n_vocab(self):
-        return 0 if self.vocab_keys is None else len(self.vocab_keys)
+        return self._n_vocab
+
+    # host copies of the fitted state, fetched from the device on first use
+    @property
+    def vocab_keys(self):
+        if self._h_vocab_keys is None and self._n_vocab and self._d_vocab is not None:
+            self._h_vocab_keys = self._d_vocab[:self._n_vocab].cpu().numpy().view(np.uint64)
+        return self._h_vocab_keys
+
+    @property
+    def df(self):
+        if self._h_df is None and self._n_vocab and self._d_df is not None:
+            self._h_df = self._d_df[:self._n_vocab].cpu().numpy().astype(np.int64)
+        return self._h_df
+
+    @property
+    def idf(self):
+        if self._h_idf is None and self._n_vocab and self._d_idf is not None:
+            self._h_idf = self._d_idf[:self._n_vocab].cpu().numpy()
+        return self._h_idf
 
     def code_space(self):
         return int(self.base) ** self.hi
@@ -203,7 +245,7 @@ class NgramTfidf:
         return stage_strings(strings, self.lo, self.hi)
 
     # ---- stage A ----------------------------------------------------------------------------------
-    def _stage_a(self, S, d_sym):
+    def _stage_a(self, S, d_sym, fit=False):
         R = _Rows()
         R.n, R.cap, R.occ_ptr = S.n, S.cap, S.occ_ptr
         R.codes = torch.empty(max(R.cap, 1), dtype=torch.int64, device=_dev())
@@ -215,10 +257,11 @@ class NgramTfidf:
         R._keep = S
         # upper bound of any row's nnz: the host-side slot bound, tightened to the true maximum (one small D2H) only when
         # the bound alone would rule out the fp32-filter kernels
-        bound = S.max_slots
-        if bound > DENSE32_MAX_ROW_NNZ and R.n:
-            bound = int(R.row_cnt[:R.n].max().item())
-        self.max_row_nnz = max(self.max_row_nnz, bound)
+        if not fit:                                           # (fit folds the true maximum into its one D2H)
+            bound = S.max_slots
+            if bound > DENSE32_MAX_ROW_NNZ and R.n:
+                bound = int(R.row_cnt[:R.n].max().item())
+            self.max_row_nnz = max(self.max_row_nnz, bound)
         return R
 
     def _fit_alphabet(self, staged, comm=None):
@@ -259,7 +302,7 @@ class NgramTfidf:
         if self.code_space() >= 2 ** 64:
             raise ValueError(f"alphabet of {self.base - 1} symbols with {self.hi}-grams exceeds 64-bit n-gram codes")
         d_sym = self._sym_table()
-        rows = [self._stage_a(S, d_sym) for S in staged]
+        rows = [self._stage_a(S, d_sym, fit=True) for S in staged]
         n_docs = sum(r.n for r, c in zip(rows, counted) if c)
         dev = _dev()
         d_nv = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -300,26 +343,38 @@ class NgramTfidf:
             d_rank = None
             ws = _ws(cap2 * 8 + 256 + _lib.load().pfz_scan_ws_bytes(cap2))
             _lib.call("pfz_vocab_from_sorted", _p(keys), cap2, _p(cursor), _p(d_vocab), _p(d_df), _p(d_nv), _p(ws), _stream())
-        V = int(d_nv.item())                                  # the one host sync of fit
+        # idf exactly as scikit-learn computes it on the host (sk:feature_extraction/text.py:1679-1694):
+        # np.log((n_samples + 1) / (df + 1)) + 1 -- same numpy, same bits as the reference on this machine -- as a TABLE over
+        # every possible df (0..n_docs), looked up on the device: no df D2H, no idf H2D, nothing waits for the host.
+        d_tab = _idf_table(n_docs)
+        d_idf = torch.empty(d_df.numel(), dtype=torch.float64, device=dev)
+        _lib.call("pfz_idf_lookup", _p(d_df), _p(d_nv), int(d_df.numel()), _p(d_tab), int(d_tab.numel()), _p(d_idf), _stream())
+        # the one small D2H (and host sync) of fit: V, sum df^2 (chooses the K2 variant), the longest row
+        dfv = d_df.double()
+        vmask = torch.arange(d_df.numel(), device=dev) < d_nv
+        mx = torch.stack([r.row_cnt[:r.n].max() if r.n else torch.zeros((), dtype=torch.int32, device=dev) for r in rows]).max()
+        stats = torch.stack([d_nv[0].double(), torch.where(vmask, dfv * dfv, torch.zeros_like(dfv)).sum(), mx.double()]).cpu().numpy()
+        V = int(stats[0])
         if V == 0:
             raise ValueError("empty vocabulary; perhaps the documents only contain stop words")
-        self.vocab_keys = d_vocab[:V].cpu().numpy().view(np.uint64)
-        self.df = d_df[:V].cpu().numpy().astype(np.int64)
+        self._n_vocab = V
+        self._sum_df_sq = float(stats[1])
+        self.max_row_nnz = max(self.max_row_nnz, int(stats[2]))
+        self._h_vocab_keys = self._h_df = self._h_idf = None
         self.n_fit_docs = n_docs
-        # idf exactly as scikit-learn computes it on the host (sk:feature_extraction/text.py:1679-1694):
-        # np.log((n_samples + 1) / (df + 1)) + 1 -- same numpy, same bits as the reference on this machine.
-        self.idf = np.log((n_docs + 1.0) / (self.df.astype(np.float64) + 1.0)) + 1.0
         self._d_vocab = d_vocab[:V]
+        self._d_df = d_df[:V]
         self._d_rank = d_rank
-        self._d_idf = _to_dev(self.idf)
+        self._d_idf = d_idf[:V]
         return rows
 
     def _ensure_device_state(self):
-        if self.vocab_keys is None:
+        if not self._n_vocab:
             raise ValueError("vectoriser is not fitted")
-        if self._d_vocab is None:
-            self._d_vocab = _to_dev(self.vocab_keys.view(np.int64))
-            self._d_idf = _to_dev(self.idf)
+        if self._d_vocab is None:                             # restored from a pickle
+            self._d_vocab = _to_dev(self._h_vocab_keys.view(np.int64))
+            self._d_idf = _to_dev(self._h_idf)
+            self._d_df = _to_dev(self._h_df.astype(np.int32))
             self._d_rank = None
             cs = self.code_space()
             if cs <= DENSE_CODE_SPACE_MAX:
@@ -346,10 +401,12 @@ class NgramTfidf:
     def density(self):
         """Postings visited per scored pair, estimated from the fitted document frequencies:
         sum_t df_t^2 / n_docs^2 (exact for a self-match).  Chooses the K2 variant."""
-        if self.df is None or not self.n_fit_docs:
+        if not self.n_fit_docs or not self._n_vocab:
             return None
-        d = self.df.astype(np.float64)
-        return float((d * d).sum() / float(self.n_fit_docs) ** 2)
+        if self._sum_df_sq is None:
+            d = self.df.astype(np.float64)
+            self._sum_df_sq = float((d * d).sum())
+        return self._sum_df_sq / float(self.n_fit_docs) ** 2
 
     def fit(self, strings):
         self.fit_rows([strings])

@@ -70,6 +70,7 @@ def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarra
     if to_list is None:
         to_list = from_list
     n, k = top_idx.shape
+    LAST_TAIL["d2h_bytes"], LAST_TAIL["device"] = int(top_idx.nbytes + top_val.nbytes), False
     # column-major working copies: every per-column array below is contiguous
     sims_t = np.round(np.ascontiguousarray(top_val.T), 3)
     idx_t = np.ascontiguousarray(top_idx.T)
@@ -107,6 +108,9 @@ def assemble_matches(from_list, to_list, top_idx: np.ndarray, top_val: np.ndarra
         cols[names[r]] = pd.Series(to_arr[idx], dtype=object)
         cols[snames[r]] = sims_t[r]
     return pd.DataFrame(cols)
+
+
+LAST_TAIL = {"d2h_bytes": 0, "device": False}               # bytes of the most recent frame tail's D2H (bench.py reports them)
 
 
 def device_tail_available(*staged):
@@ -149,6 +153,7 @@ def assemble_matches_device(from_arrow, to_blob, to_off, top_idx, top_val) -> pd
     parts = [sims.view(torch.uint8), offsets.view(torch.uint8), bitmap.view(torch.uint8), data[:total]]
     sizes = [p.numel() for p in parts]
     host = torch.cat(parts).cpu().numpy()
+    LAST_TAIL["d2h_bytes"], LAST_TAIL["device"] = int(host.nbytes) + 4, True
     o = np.cumsum([0] + sizes)
     h_sims = host[o[0]:o[1]].view(np.float64).reshape(k, n)
     h_off = host[o[1]:o[2]].view(np.int32).reshape(k, n + 1)
