@@ -361,12 +361,17 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
                     }
                     __syncthreads();
                     const int nb = min(ITEM_CAP, total - start);
+                    // each warp walks its items (w, w + W, ...) with the NEXT item's posting chunk already in flight
+                    BItem it; uint2 pk = make_uint2(0u, 0u);
+                    if (w < nb) { it = items[w]; if (lane < it.cnt) pk = __ldg(pk_lane + it.off); }
                     for (int i = w; i < nb; i += W) {
-                        const BItem it = items[i];
+                        BItem nit; uint2 npk = make_uint2(0u, 0u);
+                        nit.off = 0; nit.cnt = 0; nit.fvs = 0u; nit.nf = 0;
+                        if (i + W < nb) { nit = items[i + W]; if (lane < nit.cnt) npk = __ldg(pk_lane + nit.off); }
                         // idle lanes of a partial chunk add 0 to cell `lane` of each row (distinct banks; no predicates in the loop);
                         // active lanes add mulhi(v_i, w_i) + 1, so that every common term registers (sum > 0)
-                        unsigned jl = (unsigned)lane, wq = 0u, one = 0u;
-                        if (lane < it.cnt) { const uint2 pk = __ldg(pk_lane + it.off); jl = pk.x; wq = pk.y; one = 1u; }
+                        const bool on = lane < it.cnt;
+                        const unsigned jl = on ? pk.x : (unsigned)lane, wq = on ? pk.y : 0u, one = on ? 1u : 0u;
                         const unsigned cell = acc_s + (jl << 2);
                         const uint2 *fv = reinterpret_cast<const uint2 *>(fvtab) + it.fvs;
                         // table entries first, updates after (ptxas keeps LDS behind an earlier ATOMS): groups of 4, then the tail
@@ -385,6 +390,7 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
                             if (r > 1) red_add_u32(cell + e1.x, __umulhi(e1.y, wq) + one);
                             if (r > 2) red_add_u32(cell + e2.x, __umulhi(e2.y, wq) + one);
                         }
+                        it = nit; pk = npk;
                     }
                     __syncthreads();
                 }
