@@ -34,9 +34,12 @@ def _check(x_bf16, y_bf16, idx, val, k, min_sim=0.0, self_match=False):
             assert s[i][g].min() >= ref_sorted[i][min(len(g), cnt_ref) - 1] - 2 * TOL
 
 
+@pytest.mark.parametrize("two_cta", ["0", "1"])
 @pytest.mark.parametrize("n_from,n_to,d,k", [(6, 3, 300, 3), (300, 700, 768, 10), (129, 257, 64, 1), (1000, 2500, 96, 32), (257, 5000, 200, 5)])
-def test_dense_topk_random(n_from, n_to, d, k):
+def test_dense_topk_random(n_from, n_to, d, k, two_cta, monkeypatch):
+    """Both launch shapes: one CTA per 128 from-rows, and CTA pairs (tcgen05 cta_group::2, M = 256, half the to-operand per CTA)."""
     from polyfuzz_b200 import dense
+    monkeypatch.setenv("PFZ_K4_2CTA", two_cta)
     g = torch.Generator().manual_seed(n_from * 7 + d)
     xf = torch.randn(n_from, d, generator=g); yf = torch.randn(n_to, d, generator=g)
     nd = min(5, n_to, n_from); yf[:nd] = xf[:nd] * 3.0           # exact duplicates (up to scale) -> score 1.0
