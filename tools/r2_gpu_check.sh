@@ -1,13 +1,13 @@
 #!/bin/bash
 # Developer tool: one GPU call that exercises the round-2 kernels (tests per file, K2 sweep, bench); logs under gpurun_out/.
 mkdir -p gpurun_out
-for f in test_gpu_tfidf test_gpu_fuzz test_gpu_editdist test_gpu_dense test_gpu_dropin; do
-  echo "=== $f"; (timeout 900 python -m pytest tests/$f.py -m gpu -x -q 2>&1 | tail -15) | tee gpurun_out/r2_$f.log
+for f in test_gpu_tfidf test_gpu_fuzz test_gpu_editdist test_gpu_dropin test_gpu_dense; do
+  echo "=== $f"; (timeout -k 10 900 python -m pytest tests/$f.py -m gpu -x -q 2>&1 | tail -15) | tee gpurun_out/r2_$f.log
 done
 for cfg in "8 1024" "8 2048" "16 1024" "16 512" "8 512"; do
-  set -- $cfg; echo "rows=$1 tile=$2"; PFZ_BLOCK_ROWS=$1 timeout 300 python tools/k2_sweep.py 100000 $2 block 2>&1 | tail -1
+  set -- $cfg; echo "rows=$1 tile=$2"; PFZ_BLOCK_ROWS=$1 timeout -k 10 300 python tools/k2_sweep.py 100000 $2 block 2>&1 | tail -1
 done 2>&1 | tee gpurun_out/r2_sweep.log
-(timeout 600 python bench.py --steps 5 --warmup 3) > gpurun_out/r2_bench3.json 2> gpurun_out/r2_bench3.err; tail -3 gpurun_out/r2_bench3.err
+(timeout -k 10 600 python bench.py --steps 5 --warmup 3) > gpurun_out/r2_bench3.json 2> gpurun_out/r2_bench3.err; tail -3 gpurun_out/r2_bench3.err
 python - <<'PY'
 import json
 try:
