@@ -34,6 +34,7 @@ constexpr double K2B_SCALE = 67108864.0;         // 2^26: fixed-point unit of th
 constexpr double K2B_MARGIN = 1e-5;              // filter margin: >= 2 x 194 units (two approximate sums are compared by the lane-maxima gate)
 constexpr unsigned K2B_MARGIN_Q = 672u;          // ceil(K2B_MARGIN * 2^26)
 constexpr int ITEM_CAP = 256;                    // work items per batch
+constexpr int BLK_QCAP = 256;                    // candidates a from-row may queue before they are re-scored exactly
 constexpr int RANK_CAP = 16383;                  // term ranks are capped to 14 bits in the clustering key
 
 struct __align__(16) BlockDesc { int pos0; int nrows; int base; int nterms; };
@@ -233,7 +234,7 @@ __host__ __device__ inline size_t blk_arena_bytes(int T) {
            + (size_t)ITEM_CAP * 16             // items
            + (size_t)BF * 64 * 8               // terms + fvdesc (uint2)
            + (size_t)BF * 64 * 8               // fv
-           + (size_t)BF * 64 * 4               // candidates: 64 per warp
+           + (size_t)BF * BLK_QCAP * 4         // candidate queue of every warp (= from-row)
            + 256;                              // scan scratch, descriptor broadcast
 }
 
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
     BItem *items = reinterpret_cast<BItem *>(base);                     base += (size_t)ITEM_CAP * 16;
     uint2 *termtab = reinterpret_cast<uint2 *>(base);                   base += (size_t)FV_CAP * 8;      // {term, fvdesc}
     uint2 *fvtab = reinterpret_cast<uint2 *>(base);                     base += (size_t)FV_CAP * 8;
-    int *cand = reinterpret_cast<int *>(base) + w * 64;                 base += (size_t)BF * 64 * 4;
+    int *cand = reinterpret_cast<int *>(base) + w * BLK_QCAP;           base += (size_t)BF * BLK_QCAP * 4;
     int *wsum = reinterpret_cast<int *>(base);                          // [W] warp totals of the item scan
     int *bcast = wsum + 32;                                             // descriptor index broadcast
 
@@ -288,6 +289,10 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
         double tv = P.min_sim; int ti = -1;
         double kv = P.min_sim; int ki = -1;
         unsigned thr = thr0;
+        // the K largest fixed-point sums seen so far (lane r = r-th largest): they, not the exact list, drive the filter
+        // threshold, so that the exact re-scoring can wait until the block is done (a to-row of the final top-k has an exact
+        // score >= the K-th best exact score seen >= a_K - err, hence a sum >= a_K - 2 err > a_K - MARGIN)
+        unsigned av = 0u, akth = 0u;
         int ncand = 0;
         int nfv_total = has_row && lane == 0 ? m : 0;
         for (int u = tid; u < nterms; u += NT) termtab[u] = make_uint2((unsigned)P.blk_terms[D.base + u], (unsigned)P.blk_fvdesc[D.base + u]);
@@ -301,10 +306,10 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
         __syncthreads();
 
         // exact scoring + insertion of up to 32 queued candidates of this warp's row (one per lane)
-        auto score_round = [&](int n_round) {
+        auto score_round = [&](int off, int n_round) {
             double sc = 0.0; int j = -1; bool cnd = false;
             if (lane < n_round) {
-                const int jloc = cand[lane];
+                const int jloc = cand[off + lane];
                 const int b0 = P.b_indptr[jloc];
                 sc = blk_exact_dot(P.a_indices + a0, P.a_data + a0, m, P.b_indices + b0, P.b_data + b0, P.b_indptr[jloc + 1] - b0);
                 j = (int)(P.to_base + jloc);
@@ -328,6 +333,15 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
                 cm = __ballot_sync(FULL, cnd);
             }
             if (ki >= 0) thr = blk_thr_q(kv);
+        };
+        auto drain = [&]() {                                // exact re-scoring of the queue, 32 candidates per round, newest first
+            while (ncand > 0) {
+                const int n_round = min(32, ncand);
+                __syncwarp();
+                score_round(ncand - n_round, n_round);
+                ncand -= n_round;
+            }
+            __syncwarp();
         };
 
         for (int tau = tau_lo; tau < tau_hi; ++tau) {
@@ -400,9 +414,9 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
             if (has_row) {
                 uint4 *rowp = reinterpret_cast<uint4 *>(acc + (size_t)w * T);
                 if (stau == tau) { if (lane == 0) acc[(size_t)w * T + sjl] = 0u; __syncwarp(); }   // the diagonal never competes
-                unsigned gate = thr;
-                if (ki < 0) {
-                    // list not full yet: the K-th largest of the 32 lane maxima bounds the unit's K-th best score from below
+                unsigned gate = max(thr, akth > K2B_MARGIN_Q ? akth - K2B_MARGIN_Q : 0u);
+                if (akth == 0u) {
+                    // fewer than K sums seen: the K-th largest of the 32 lane maxima bounds the unit's K-th best sum from below
                     unsigned mx = 0u;
                     for (int c = lane; c < (T >> 2); c += 32) { const uint4 v = rowp[c]; mx = max(max(mx, max(v.x, v.y)), max(v.z, v.w)); }
                     const unsigned srt = warp_sort_desc_u32(mx, lane);
@@ -419,29 +433,30 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
                     for (int comp = 0; comp < 4; ++comp) {
                         const unsigned x = comp == 0 ? v.x : comp == 1 ? v.y : comp == 2 ? v.z : v.w;
                         const bool take = x > gate;
-                        const unsigned tm = __ballot_sync(FULL, take);
+                        unsigned tm = __ballot_sync(FULL, take);
                         if (tm == 0u) continue;
+                        if (ncand + 32 > BLK_QCAP) drain();                 // (rare: > 224 contenders of one row inside one block)
                         if (take) cand[ncand + __popc(tm & lt)] = tau * T + c * 4 + comp;
                         ncand += __popc(tm);
-                        __syncwarp();
-                        if (ncand >= 32) {
-                            score_round(32);
-                            __syncwarp();
-                            const int rest = ncand - 32;
-                            int mv = 0;
-                            if (lane < rest) mv = cand[32 + lane];
-                            __syncwarp();
-                            if (lane < rest) cand[lane] = mv;
-                            ncand = rest;
-                            __syncwarp();
+                        // the K largest sums so far -> filter threshold
+                        while (tm) {
+                            const int src = __ffs(tm) - 1; tm &= tm - 1;
+                            const unsigned cx = __shfl_sync(FULL, x, src);
+                            if (cx <= akth) continue;
+                            const int pos = __popc(__ballot_sync(FULL, (lane < K) && av >= cx));
+                            const unsigned up = __shfl_up_sync(FULL, av, 1);
+                            if (lane > pos) av = up; else if (lane == pos) av = cx;
+                            akth = __shfl_sync(FULL, av, K - 1);
                         }
+                        if (akth > K2B_MARGIN_Q) gate = max(gate, akth - K2B_MARGIN_Q);
+                        __syncwarp();
                     }
                 }
             }
             __syncthreads();
         }
         if (has_row) {
-            if (ncand > 0) { __syncwarp(); score_round(ncand); __syncwarp(); }
+            drain();                                            // all warps of the CTA re-score their rows' contenders concurrently
             if (lane < K) {
                 const size_t o = ((size_t)split * P.n_from + row) * K + lane;
                 P.top_idx[o] = ti;

@@ -67,23 +67,6 @@ def torch_full_like_int(t):
     import torch
     return torch.full_like(t, -1)
 
-_NAMES = {"ratio": "ratio", "levenshtein": "norm_lev", "norm_lev": "norm_lev", "normalized_similarity": "norm_lev",
-          "normalized_levenshtein": "norm_lev"}
-
-
-def _resolve_scorer(scorer) -> str:
-    if scorer is None:
-        return "ratio"
-    if isinstance(scorer, str):
-        key = scorer.lower()
-    else:
-        key = getattr(scorer, "__name__", "")
-    if key in _NAMES:
-        return _NAMES[key]
-    raise NotImplementedError(f"scorer {scorer!r} has no GPU implementation (supported: 'ratio', 'levenshtein'); "
-                              "polyfuzz_b200 has no CPU fallback")
-
-
 class RapidFuzz(BaseMatcher):
     """Edit-distance matcher (GPU).  Arguments as in the reference: n_jobs (accepted, ignored -- the GPU
     scores all pairs in one launch), score_cutoff in [0,1], scorer (default fuzz.WRatio, as the reference), model_id."""
