@@ -38,14 +38,24 @@ struct HashParams {
 };
 
 __device__ __forceinline__ bool h_key_before(double sa, int ia, double sb, int ib) { return (sa > sb) || (sa == sb && ia < ib); }
-__device__ __forceinline__ double h_exact_dot(const int32_t *__restrict__ ai, const double *__restrict__ av, int an,
-                                              const int32_t *__restrict__ bi, const double *__restrict__ bv, int bn) {
+// canonical score of (from-row a, to-row b): common terms in ascending order, product rounded, then added.  The to-row is
+// staged 32 entries at a time with INDEPENDENT loads (one memory latency per chunk instead of one per merge step -- the merge
+// itself chases pointers), then merged against the from-row.
+__device__ __noinline__ double h_exact_dot(const int32_t *__restrict__ ai, const double *__restrict__ av, int an,
+                                  const int32_t *__restrict__ bi, const double *__restrict__ bv, int bn) {
     double s = 0.0;
-    int p = 0, q = 0;
-    while (p < an && q < bn) {
-        const int ca = ai[p], cb = bi[q];
-        if (ca == cb) { s = __dadd_rn(s, __dmul_rn(av[p], bv[q])); ++p; ++q; }
-        else if (ca < cb) ++p; else ++q;
+    int p = 0;
+    for (int c0 = 0; c0 < bn && p < an; c0 += 32) {
+        int ci[32]; double cv[32];                          // local memory (dynamically indexed): registers stay with the hot loop
+        const int nc = min(32, bn - c0);
+#pragma unroll 8
+        for (int q = 0; q < nc; ++q) { ci[q] = bi[c0 + q]; cv[q] = bv[c0 + q]; }
+#pragma unroll 1
+        for (int q = 0; q < nc; ++q) {
+            const int cb = ci[q];
+            while (p < an && ai[p] < cb) ++p;
+            if (p < an && ai[p] == cb) { s = __dadd_rn(s, __dmul_rn(av[p], cv[q])); ++p; }
+        }
     }
     return s;
 }
