@@ -358,16 +358,18 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
             bool any_post = false;
             for (int tb = 0; tb < nterms; tb += NT) {
                 const int u = tb + tid;
-                int s = 0, len = 0; unsigned fvd = 0u;
-                if (u < nterms) {
-                    const uint2 tt = termtab[u];
-                    fvd = tt.y;
-                    const int64_t c = (int64_t)tt.x * n_tiles + tau;
-                    s = seg[c];
-                    len = seg[c + 1] - s;
+                int s = 0, len = 0, nch = 0, incl = 0; unsigned fvd = 0u;
+                if (tb + (w << 5) < nterms) {                     // (warp-uniform: a block has ~50 terms, warps 2..7 usually skip this)
+                    if (u < nterms) {
+                        const uint2 tt = termtab[u];
+                        fvd = tt.y;
+                        const int64_t c = (int64_t)tt.x * n_tiles + tau;
+                        s = seg[c];
+                        len = seg[c + 1] - s;
+                    }
+                    nch = (len + 31) >> 5;
+                    incl = warp_incl_scan(nch);
                 }
-                const int nch = (len + 31) >> 5;
-                const int incl = warp_incl_scan(nch);
                 if (lane == 31) wsum[w] = incl;
                 __syncthreads();
                 int woff = 0, total = 0;
