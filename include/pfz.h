@@ -173,6 +173,8 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
  *   post_pk: uint2[nnz] = {tile-local row, round(weight * 2^26)} in segment order (pfz_index_pack_q26 of an index built with
  *            PFZ_INDEX_BANK_ORDER32); tile: multiple of 128; k <= 32; from-rows <= 128 terms each (*err_flag_dev is set to 1
  *            otherwise); n_from < 2^22.
+ *   acc_bits: 32 (one fixed-point accumulator per word, unit 2^-26) or 16 (two per word, unit 2^-15: twice the tile in the same
+ *            shared memory, coarser filter; tile must be a multiple of 256).
  *   nnz_cap_from: capacity of a_indices / a_data (>= nnz).  ws: >= pfz_spcos_block_ws_bytes(...) bytes.
  *   Output as pfz_spcos_topk: [n_splits][n_from][k] partial lists (pfz_topk_merge when n_splits > 1).                    */
 int64_t pfz_spcos_block_ws_bytes(int32_t n_from, int64_t nnz_cap_from, int32_t n_vocab, int32_t n_splits);
@@ -180,8 +182,8 @@ int pfz_index_pack_q26(const uint16_t *post_idx, const double *post_val, const i
 int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from, int64_t nnz_cap_from,
                          const int32_t *seg, const void *post_pk, const int32_t *b_indptr, const int32_t *b_indices, const double *b_data,
                          int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to, int32_t k, double min_similarity, int32_t self_match,
-                         int64_t from_index_base, int64_t to_index_base, int32_t n_splits, int32_t block_rows, int32_t *top_idx,
-                         double *top_val, int32_t *err_flag_dev, void *ws, void *stream);
+                         int64_t from_index_base, int64_t to_index_base, int32_t n_splits, int32_t block_rows, int32_t acc_bits,
+                         int32_t *top_idx, double *top_val, int32_t *err_flag_dev, void *ws, void *stream);
 
 /* PFZ_K2_HASH -- sparse-regime variant of K2 (csrc/pfz_spcos_hash.cu): one CTA per from-row accumulates the postings the row
  * visits in a shared-memory hash table keyed by the to-row (atom.shared.cas + red.shared.add.u32, fixed point 2^-26), scans

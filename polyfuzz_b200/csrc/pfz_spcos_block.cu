@@ -238,9 +238,9 @@ __device__ __forceinline__ unsigned warp_sort_desc_u32(unsigned x, int lane) {
 }
 
 // per-CTA shared-memory arena (bytes), T = tile
-template <int BF>
+template <int BF, bool P16>
 __host__ __device__ inline size_t blk_arena_bytes(int T) {
-    return (size_t)BF * T * 4                  // acc
+    return (size_t)BF * T * (P16 ? 2 : 4)      // acc
            + (size_t)ITEM_CAP * 16             // items
            + (size_t)BF * 64 * 8               // terms + fvdesc (uint2)
            + (size_t)BF * 64 * 8               // fv
@@ -248,7 +248,11 @@ __host__ __device__ inline size_t blk_arena_bytes(int T) {
            + 256;                              // scan scratch, descriptor broadcast
 }
 
-template <int BF>
+// P16: two 16-bit fixed-point accumulators (unit 2^-15) per 32-bit word -- to-rows j and j + tile/2 share a word, so the bank
+// of an update is still (row mod 32) -- which doubles the tile a CTA can hold (half the (block, tile) units, longer posting
+// segments) at a coarser filter: per product -0.52 < update - v*w*2^15 <= 1.51 units, margin 3*m + 2 units for a from-row
+// of m terms (m <= 128: every 16-bit half stays below 2^15 + 194 < 2^16, no carry into its neighbour).
+template <int BF, bool P16>
 __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams P) {
     constexpr int W = BF, NT = BF * 32, FV_CAP = BF * 64;
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -256,7 +260,8 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
     const unsigned lt = (1u << lane) - 1u;
     const int T = P.tile, K = P.k;
     unsigned char *base = dyn;
-    unsigned *acc = reinterpret_cast<unsigned *>(base);                 base += (size_t)BF * T * 4;
+    const int TW = P16 ? (T >> 1) : T;                                 // 32-bit accumulator words per from-row
+    unsigned *acc = reinterpret_cast<unsigned *>(base);                 base += (size_t)BF * TW * 4;
     BItem *items = reinterpret_cast<BItem *>(base);                     base += (size_t)ITEM_CAP * 16;
     uint2 *termtab = reinterpret_cast<uint2 *>(base);                   base += (size_t)FV_CAP * 8;      // {term, fvdesc}
     uint2 *fvtab = reinterpret_cast<uint2 *>(base);                     base += (size_t)FV_CAP * 8;
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
     int *wsum = reinterpret_cast<int *>(base);                          // [W] warp totals of the item scan
     int *bcast = wsum + 32;                                             // descriptor index broadcast
 
-    for (int q = tid; q < BF * T; q += NT) acc[q] = 0u;
+    for (int q = tid; q < BF * TW; q += NT) acc[q] = 0u;
     const unsigned acc_s = sm_u32(acc);
     const uint2 *pk_lane = P.post_pk + lane;
     const int32_t *__restrict__ seg = P.seg;
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
     const int tau_lo = split * tiles_per;
     const int tau_hi = min(P.n_tiles, tau_lo + tiles_per);
     int32_t *counter = P.counter + split;
-    const unsigned thr0 = blk_thr_q(fmax(P.min_sim, 0.0));
+    const double scale = P16 ? 32768.0 : K2B_SCALE;
     __syncthreads();
 
     for (;;) {
@@ -298,7 +303,10 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
         }
         double tv = P.min_sim; int ti = -1;
         double kv = P.min_sim; int ki = -1;
-        unsigned thr = thr0;
+        // filter margin in accumulator units, and the largest value not above (x - margin)
+        const unsigned MQ = P16 ? (unsigned)(3 * m + 2) : K2B_MARGIN_Q;
+        auto thr_of = [&](double x) { const double y = x * scale - (double)MQ; return y <= 0.0 ? 0u : (unsigned)__double2ll_rd(y); };
+        unsigned thr = thr_of(fmax(P.min_sim, 0.0));
         // the K largest fixed-point sums seen so far (lane r = r-th largest): they, not the exact list, drive the filter
         // threshold, so that the exact re-scoring can wait until the block is done (a to-row of the final top-k has an exact
         // score >= the K-th best exact score seen >= a_K - err, hence a sum >= a_K - 2 err > a_K - MARGIN)
@@ -342,7 +350,7 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
                 cnd = cnd && lane != src && blk_key_before(sc, j, kv, ki);
                 cm = __ballot_sync(FULL, cnd);
             }
-            if (ki >= 0) thr = blk_thr_q(kv);
+            if (ki >= 0) thr = thr_of(kv);
         };
         auto drain = [&]() {                                // exact re-scoring of the queue, 32 candidates per round, newest first
             while (ncand > 0) {
@@ -397,24 +405,26 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
                         // idle lanes of a partial chunk add 0 to cell `lane` of each row (distinct banks; no predicates in the loop);
                         // active lanes add mulhi(v_i, w_i) + 1, so that every common term registers (sum > 0)
                         const bool on = lane < it.cnt;
-                        const unsigned jl = on ? pk.x : (unsigned)lane, wq = on ? pk.y : 0u, one = on ? 1u : 0u;
-                        const unsigned cell = acc_s + (jl << 2);
+                        const unsigned jl = on ? pk.x : (unsigned)lane, one = on ? 1u : 0u;
+                        const unsigned wq = on ? (P16 ? ((pk.y + 1024u) >> 11) : pk.y) : 0u;       // 2^-15 units when packed
+                        const unsigned hi = P16 && jl >= (unsigned)TW ? 16u : 0u;                  // upper half-word: to-rows tile/2 ..
+                        const unsigned cell = acc_s + ((P16 ? (hi ? jl - (unsigned)TW : jl) : jl) << 2);
                         const uint2 *fv = reinterpret_cast<const uint2 *>(fvtab) + it.fvs;
                         // table entries first, updates after (ptxas keeps LDS behind an earlier ATOMS): groups of 4, then the tail
                         int q = 0;
                         for (; q + 4 <= it.nf; q += 4) {
                             const uint2 e0 = fv[q], e1 = fv[q + 1], e2 = fv[q + 2], e3 = fv[q + 3];
-                            red_add_u32(cell + e0.x, __umulhi(e0.y, wq) + one);
-                            red_add_u32(cell + e1.x, __umulhi(e1.y, wq) + one);
-                            red_add_u32(cell + e2.x, __umulhi(e2.y, wq) + one);
-                            red_add_u32(cell + e3.x, __umulhi(e3.y, wq) + one);
+                            red_add_u32(cell + e0.x, (__umulhi(e0.y, wq) + one) << hi);
+                            red_add_u32(cell + e1.x, (__umulhi(e1.y, wq) + one) << hi);
+                            red_add_u32(cell + e2.x, (__umulhi(e2.y, wq) + one) << hi);
+                            red_add_u32(cell + e3.x, (__umulhi(e3.y, wq) + one) << hi);
                         }
                         const int r = it.nf - q;
                         if (r > 0) {
                             const uint2 e0 = fv[q], e1 = fv[q + (r > 1 ? 1 : 0)], e2 = fv[q + (r > 2 ? 2 : 0)];
-                            red_add_u32(cell + e0.x, __umulhi(e0.y, wq) + one);
-                            if (r > 1) red_add_u32(cell + e1.x, __umulhi(e1.y, wq) + one);
-                            if (r > 2) red_add_u32(cell + e2.x, __umulhi(e2.y, wq) + one);
+                            red_add_u32(cell + e0.x, (__umulhi(e0.y, wq) + one) << hi);
+                            if (r > 1) red_add_u32(cell + e1.x, (__umulhi(e1.y, wq) + one) << hi);
+                            if (r > 2) red_add_u32(cell + e2.x, (__umulhi(e2.y, wq) + one) << hi);
                         }
                         it = nit; pk = npk;
                     }
@@ -424,31 +434,43 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
             if (!__syncthreads_or(any_post)) continue;
             // scan + clear: warp w scans the accumulators of its row against the row's threshold
             if (has_row) {
-                uint4 *rowp = reinterpret_cast<uint4 *>(acc + (size_t)w * T);
-                if (stau == tau) { if (lane == 0) acc[(size_t)w * T + sjl] = 0u; __syncwarp(); }   // the diagonal never competes
-                unsigned gate = max(thr, akth > K2B_MARGIN_Q ? akth - K2B_MARGIN_Q : 0u);
+                uint4 *rowp = reinterpret_cast<uint4 *>(acc + (size_t)w * TW);
+                if (stau == tau) {                                     // the diagonal never competes
+                    if (lane == 0) {
+                        if (P16) acc[(size_t)w * TW + (sjl >= TW ? sjl - TW : sjl)] &= (sjl >= TW ? 0x0000ffffu : 0xffff0000u);
+                        else acc[(size_t)w * TW + sjl] = 0u;
+                    }
+                    __syncwarp();
+                }
+                // largest accumulator of a word group: plain maximum, or the maximum over the 16-bit halves
+                auto wmax = [&](const uint4 &v) -> unsigned {
+                    if (!P16) return max(max(v.x, v.y), max(v.z, v.w));
+                    const unsigned m2 = __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w));
+                    return max(m2 & 0xffffu, m2 >> 16);
+                };
+                unsigned gate = max(thr, akth > MQ ? akth - MQ : 0u);
                 if (akth == 0u) {
                     // fewer than K sums seen: the K-th largest of the 32 lane maxima bounds the unit's K-th best sum from below
                     unsigned mx = 0u;
-                    for (int c = lane; c < (T >> 2); c += 32) { const uint4 v = rowp[c]; mx = max(max(mx, max(v.x, v.y)), max(v.z, v.w)); }
+                    for (int c = lane; c < (TW >> 2); c += 32) mx = max(mx, wmax(rowp[c]));
                     const unsigned srt = warp_sort_desc_u32(mx, lane);
                     const unsigned kth = __shfl_sync(FULL, srt, K - 1);
-                    if (kth > K2B_MARGIN_Q) gate = max(gate, kth - K2B_MARGIN_Q);
+                    if (kth > MQ) gate = max(gate, kth - MQ);
                 }
                 const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                for (int c0 = 0; c0 < (T >> 2); c0 += 32) {
+                for (int c0 = 0; c0 < (TW >> 2); c0 += 32) {
                     const int c = c0 + lane;
                     const uint4 v = rowp[c]; rowp[c] = z;
-                    const unsigned mx = max(max(v.x, v.y), max(v.z, v.w));
-                    if (!__any_sync(FULL, mx > gate)) continue;
+                    if (!__any_sync(FULL, wmax(v) > gate)) continue;
 #pragma unroll
-                    for (int comp = 0; comp < 4; ++comp) {
-                        const unsigned x = comp == 0 ? v.x : comp == 1 ? v.y : comp == 2 ? v.z : v.w;
+                    for (int comp = 0; comp < (P16 ? 8 : 4); ++comp) {
+                        const unsigned word = (comp & 3) == 0 ? v.x : (comp & 3) == 1 ? v.y : (comp & 3) == 2 ? v.z : v.w;
+                        const unsigned x = P16 ? (comp < 4 ? (word & 0xffffu) : (word >> 16)) : word;
                         const bool take = x > gate;
                         unsigned tm = __ballot_sync(FULL, take);
                         if (tm == 0u) continue;
                         if (ncand + 32 > BLK_QCAP) drain();                 // (rare: > 224 contenders of one row inside one block)
-                        if (take) cand[ncand + __popc(tm & lt)] = tau * T + c * 4 + comp;
+                        if (take) cand[ncand + __popc(tm & lt)] = tau * T + c * 4 + (comp & 3) + (comp >= 4 ? TW : 0);
                         ncand += __popc(tm);
                         // the K largest sums so far -> filter threshold
                         while (tm) {
@@ -460,7 +482,7 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
                             if (lane > pos) av = up; else if (lane == pos) av = cx;
                             akth = __shfl_sync(FULL, av, K - 1);
                         }
-                        if (akth > K2B_MARGIN_Q) gate = max(gate, akth - K2B_MARGIN_Q);
+                        if (akth > MQ) gate = max(gate, akth - MQ);
                         __syncwarp();
                     }
                 }
@@ -510,18 +532,18 @@ static BlockWs block_ws_layout(int64_t n_from, int64_t nnz_cap, int64_t n_vocab,
     return L;
 }
 
-template <int BF>
+template <int BF, bool P16>
 static int launch_block(const BlockParams &P, int n_groups, int sms, int smem_max, cudaStream_t st) {
-    const size_t arena = (blk_arena_bytes<BF>(P.tile) + 15) & ~(size_t)15;
+    const size_t arena = (blk_arena_bytes<BF, P16>(P.tile) + 15) & ~(size_t)15;
     PFZ_REQUIRE(arena <= (size_t)smem_max, "pfz_spcos_topk_block: tile %d x %d rows needs %zu B shared memory > %d available", P.tile, BF, arena, smem_max);
-    PFZ_CUDA_OK(cudaFuncSetAttribute(spcos_block_kernel<BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)arena));
+    PFZ_CUDA_OK(cudaFuncSetAttribute(spcos_block_kernel<BF, P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)arena));
     int occ = 0;
-    PFZ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spcos_block_kernel<BF>, BF * 32, arena));
+    PFZ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spcos_block_kernel<BF, P16>, BF * 32, arena));
     if (occ < 1) occ = 1;
     int gx = sms * occ;
     if (gx > 2 * n_groups) gx = 2 * n_groups;
     if (P.n_splits > 1) { gx = (gx + P.n_splits - 1) / P.n_splits; if (gx < 1) gx = 1; }
-    spcos_block_kernel<BF><<<dim3(gx, P.n_splits), BF * 32, arena, st>>>(P);
+    spcos_block_kernel<BF, P16><<<dim3(gx, P.n_splits), BF * 32, arena, st>>>(P);
     PFZ_LAUNCH_OK();
     return 0;
 }
@@ -545,11 +567,12 @@ int pfz_index_pack_q26(const uint16_t *post_idx, const double *post_val, const i
 int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from, int64_t nnz_cap_from,
                          const int32_t *seg, const void *post_pk, const int32_t *b_indptr, const int32_t *b_indices, const double *b_data,
                          int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to, int32_t k, double min_similarity, int32_t self_match,
-                         int64_t from_index_base, int64_t to_index_base, int32_t n_splits, int32_t block_rows, int32_t *top_idx, double *top_val,
-                         int32_t *err_flag_dev, void *ws, void *stream) {
+                         int64_t from_index_base, int64_t to_index_base, int32_t n_splits, int32_t block_rows, int32_t acc_bits, int32_t *top_idx,
+                         double *top_val, int32_t *err_flag_dev, void *ws, void *stream) {
     PFZ_REQUIRE(k >= 1 && k <= 32, "pfz_spcos_topk_block: k=%d unsupported (1..32)", k);
     PFZ_REQUIRE(tile >= 128 && tile <= 4096 && (tile % 128) == 0, "pfz_spcos_topk_block: tile %d must be a multiple of 128 in 128..4096", tile);
     PFZ_REQUIRE(block_rows == 8 || block_rows == 16, "pfz_spcos_topk_block: block_rows %d must be 8 or 16", block_rows);
+    PFZ_REQUIRE(acc_bits == 32 || (acc_bits == 16 && tile % 256 == 0), "pfz_spcos_topk_block: acc_bits %d must be 32, or 16 with a tile that is a multiple of 256", acc_bits);
     PFZ_REQUIRE(n_splits >= 1 && n_splits <= n_tiles, "pfz_spcos_topk_block: n_splits %d out of range", n_splits);
     PFZ_REQUIRE(n_from < (1 << 22), "pfz_spcos_topk_block: n_from %d exceeds the 22-bit row id of the clustering key", n_from);
     PFZ_REQUIRE(n_vocab < (1 << 28), "pfz_spcos_topk_block: n_vocab too large");
@@ -586,16 +609,17 @@ int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, cons
     PFZ_LAUNCH_OK();
     if (scan_exclusive_i32(pos_ptr, pos_ptr, (int64_t)n_from + 1, w + L.scan_ws, st)) return 1;
     if (block_rows == 8)
-        blk_table_kernel<8><<<blk_grid((int64_t)n_groups * 32, 128, 148 * 16), 128, 0, st>>>(a_indptr, a_indices, a_data, n_from, perm, pos_ptr, tile * 4,
+        blk_table_kernel<8><<<blk_grid((int64_t)n_groups * 32, 128, 148 * 16), 128, 0, st>>>(a_indptr, a_indices, a_data, n_from, perm, pos_ptr, tile * (acc_bits == 16 ? 2 : 4),
                                                                                              blk_terms, blk_fvdesc, blk_fv, descs, n_groups, err_flag_dev);
     else
-        blk_table_kernel<16><<<blk_grid((int64_t)n_groups * 32, 64, 148 * 16), 128, 0, st>>>(a_indptr, a_indices, a_data, n_from, perm, pos_ptr, tile * 4,
+        blk_table_kernel<16><<<blk_grid((int64_t)n_groups * 32, 64, 148 * 16), 128, 0, st>>>(a_indptr, a_indices, a_data, n_from, perm, pos_ptr, tile * (acc_bits == 16 ? 2 : 4),
                                                                                               blk_terms, blk_fvdesc, blk_fv, descs, n_groups, err_flag_dev);
     PFZ_LAUNCH_OK();
     PFZ_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t) * (size_t)n_splits, st));
     BlockParams P{a_indptr, a_indices, a_data, n_from, perm, descs, 2 * n_groups, blk_terms, blk_fvdesc, blk_fv, seg,
                   reinterpret_cast<const uint2 *>(post_pk), b_indptr, b_indices, b_data, tile, n_tiles, n_to, k, min_similarity, self_match,
                   from_index_base, to_index_base, n_splits, top_idx, top_val, counters};
-    return block_rows == 8 ? launch_block<8>(P, n_groups, sms, smem_max, st) : launch_block<16>(P, n_groups, sms, smem_max, st);
+    if (acc_bits == 16) return block_rows == 8 ? launch_block<8, true>(P, n_groups, sms, smem_max, st) : launch_block<16, true>(P, n_groups, sms, smem_max, st);
+    return block_rows == 8 ? launch_block<8, false>(P, n_groups, sms, smem_max, st) : launch_block<16, false>(P, n_groups, sms, smem_max, st);
 }
 }

@@ -423,6 +423,7 @@ DEFAULT_TILE = {"list": int(os.environ.get("PFZ_TILE_LIST", "512")), "dense": in
                 "hash": 65536}
 BLOCK_TILE_STEP, BLOCK_TILE_MAX = 128, 4096
 BLOCK_ROWS = int(os.environ.get("PFZ_BLOCK_ROWS", "8"))           # from-rows (= warps) per CTA of the block kernel: 8 or 16
+BLOCK_ACC_BITS = int(os.environ.get("PFZ_BLOCK_ACC_BITS", "32"))  # 32: one accumulator per word (2^-26); 16: two per word (2^-15)
 
 
 class SparseIndex:
@@ -520,7 +521,7 @@ def _spcos_block(a, index, k, min_similarity, self_match, from_index_base, to_in
     tv = torch.empty((n_splits, max(n_from, 1), k), dtype=torch.float64, device=dev)
     _lib.call("pfz_spcos_topk_block", _p(a.indptr), _p(a.indices), _p(a.data), n_from, nnz_cap, _p(index.seg), _p(index.post_pk),
               _p(index.csr.indptr), _p(index.csr.indices), _p(index.csr.data), index.n_vocab, index.tile, index.n_tiles, index.n_to, k,
-              float(min_similarity), int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, BLOCK_ROWS, _p(ti), _p(tv), _p(err),
+              float(min_similarity), int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, BLOCK_ROWS, BLOCK_ACC_BITS if index.tile % 256 == 0 else 32, _p(ti), _p(tv), _p(err),
               _p(ws), _stream())
     if n_splits > 1:
         oi = torch.empty((max(n_from, 1), k), dtype=torch.int32, device=dev)

@@ -296,13 +296,15 @@ def test_shard_emulation_equals_unsharded(pf):
     assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
 
 
-@pytest.mark.parametrize("variant", ["dense32", "block"])
+@pytest.mark.parametrize("variant", ["dense32", "block", "block16"])
 def test_dense32_many_exact_ties_and_identical_rows(pf, monkeypatch, variant):
     """The fp32 filter must hand every row near the k-th key to the exact re-scoring: lists full of duplicates
     (scores exactly 1.0 and large groups of exactly tied scores)."""
     polyfuzz_b200, engine = pf
+    if variant == "block16":
+        monkeypatch.setattr(engine, "BLOCK_ACC_BITS", 16); variant = "block"
     _force_variant(monkeypatch, engine, variant)
-    names = ["acme holdings inc"] * 40 + ["acme holding inc"] * 40 + [f"zeta {i % 5} llc" for i in range(300)] + ["unique name ltd"]
+    names = ["acme holdings inc"] * 40 + ["dup dup llc"] * 600 + ["acme holding inc"] * 40 + [f"zeta {i % 5} llc" for i in range(300)] + ["unique name ltd"]
     m = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=12)
     idx, val, k = m.match_arrays(names)
     a = m.tf_idf_to.to_scipy()
@@ -378,12 +380,15 @@ def test_titles_slice_vectoriser_matches_reference_on_gpu(pf, golden_dir, tag, r
         _csr_eq(v.emit(rows), g[f"{tag}_{name}_indptr"], g[f"{tag}_{name}_indices"], g[f"{tag}_{name}_data"], g[f"{tag}_{name}_shape"])
 
 
-def test_block_variant_long_rows_split_blocks_and_margin(pf, monkeypatch):
+@pytest.mark.parametrize("acc_bits,rows", [(32, 8), (16, 8), (16, 16), (32, 16)])
+def test_block_variant_long_rows_split_blocks_and_margin(pf, monkeypatch, acc_bits, rows):
     """The from-row-block kernel at its contract's edge: rows of ~100-128 distinct trigrams (blocks of 8 such rows exceed the
     512-entry block table and are split in halves), mixed with short rows, duplicates and empty rows; tile 128 and a tile
     split.  The fp32 filter (margin 3e-5) must still hand every contender to the exact re-scoring."""
     polyfuzz_b200, engine = pf
     from polyfuzz_b200 import synth
+    monkeypatch.setattr(engine, "BLOCK_ACC_BITS", acc_bits)
+    monkeypatch.setattr(engine, "BLOCK_ROWS", rows)
     rng = np.random.default_rng(5)
     words = synth.company_names(400, seed=12)
     long_rows = [" ".join(rng.choice(words, 5)) for _ in range(300)]
@@ -394,7 +399,7 @@ def test_block_variant_long_rows_split_blocks_and_margin(pf, monkeypatch):
     nnz = np.diff(a.indptr)
     assert 100 < nnz.max() <= 128, nnz.max()
     oi, ov = onative.spdot_topn(a, a, 10, 0.0, self_match=True, n_threads=8)
-    for tile, splits in ((128, 1), (1024, 1), (512, 3)):
+    for tile, splits in ((128, 1), (1024, 1), (512, 3), (256, 1), (2048, 1)):
         ix = engine.SparseIndex(csr, tile=tile, variant="block")
         idx, val = engine.spcos_topk(csr, ix, 10, 0.0, self_match=True, n_splits=splits)
         assert int(ix._block_err.item()) == 0
