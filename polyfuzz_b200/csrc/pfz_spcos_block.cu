@@ -196,6 +196,15 @@ __device__ __forceinline__ void red_add_u32(unsigned a, unsigned v) {
     // of the kernel is separated from the updates by __syncthreads()
     asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(v));
 }
+// one posting chunk applied to the N from-rows that hold the term: the N table entries first, the N updates after
+template <int N, bool P16>
+__device__ __forceinline__ void red_group(unsigned cell, const uint2 *fv, unsigned wq, unsigned one, unsigned hi) {
+    uint2 e[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) e[q] = fv[q];
+#pragma unroll
+    for (int q = 0; q < N; ++q) red_add_u32(cell + e[q].x, P16 ? ((__umulhi(e[q].y, wq) + one) << hi) : (__umulhi(e[q].y, wq) + one));
+}
 __device__ __forceinline__ bool blk_key_before(double sa, int ia, double sb, int ib) { return (sa > sb) || (sa == sb && ia < ib); }
 // canonical score of (from-row a, to-row b): common terms in ascending order, product rounded, then added.  The to-row is
 // staged 32 entries at a time with INDEPENDENT loads (one memory latency per chunk instead of one per merge step -- the merge
@@ -241,7 +250,7 @@ __device__ __forceinline__ unsigned warp_sort_desc_u32(unsigned x, int lane) {
 template <int BF, bool P16>
 __host__ __device__ inline size_t blk_arena_bytes(int T) {
     return (size_t)BF * T * (P16 ? 2 : 4)      // acc
-           + (size_t)ITEM_CAP * 16             // items
+           + (size_t)(ITEM_CAP + BF) * 16      // items (+ one padding item per warp)
            + (size_t)BF * 64 * 8               // terms + fvdesc (uint2)
            + (size_t)BF * 64 * 8               // fv
            + (size_t)BF * BLK_QCAP * 4         // candidate queue of every warp (= from-row)
@@ -253,7 +262,7 @@ __host__ __device__ inline size_t blk_arena_bytes(int T) {
 // segments) at a coarser filter: per product -0.52 < update - v*w*2^15 <= 1.51 units, margin 3*m + 2 units for a from-row
 // of m terms (m <= 128: every 16-bit half stays below 2^15 + 194 < 2^16, no carry into its neighbour).
 template <int BF, bool P16>
-__global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams P) {
+__global__ void __launch_bounds__(BF * 32, BF == 8 ? 4 : 2) spcos_block_kernel(const BlockParams P) {
     constexpr int W = BF, NT = BF * 32, FV_CAP = BF * 64;
     extern __shared__ __align__(16) unsigned char dyn[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
     unsigned char *base = dyn;
     const int TW = P16 ? (T >> 1) : T;                                 // 32-bit accumulator words per from-row
     unsigned *acc = reinterpret_cast<unsigned *>(base);                 base += (size_t)BF * TW * 4;
-    BItem *items = reinterpret_cast<BItem *>(base);                     base += (size_t)ITEM_CAP * 16;
+    BItem *items = reinterpret_cast<BItem *>(base);                     base += (size_t)(ITEM_CAP + BF) * 16;
     uint2 *termtab = reinterpret_cast<uint2 *>(base);                   base += (size_t)FV_CAP * 8;      // {term, fvdesc}
     uint2 *fvtab = reinterpret_cast<uint2 *>(base);                     base += (size_t)FV_CAP * 8;
     int *cand = reinterpret_cast<int *>(base) + w * BLK_QCAP;           base += (size_t)BF * BLK_QCAP * 4;
@@ -380,9 +389,13 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
                 }
                 if (lane == 31) wsum[w] = incl;
                 __syncthreads();
-                int woff = 0, total = 0;
-#pragma unroll
-                for (int q = 0; q < W; ++q) { const int x = wsum[q]; if (q < w) woff += x; total += x; }
+                int woff, total;
+                {
+                    const int x = lane < W ? wsum[lane] : 0;       // per-warp item counts -> this warp's offset and the unit's total
+                    const int xs = warp_incl_scan(x);
+                    woff = __shfl_sync(FULL, xs - x, w);
+                    total = __shfl_sync(FULL, xs, W - 1);
+                }
                 if (total == 0) { __syncthreads(); continue; }
                 any_post = true;
                 const int first = woff + incl - nch;                  // id of this thread's first work item
@@ -393,15 +406,16 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
                         const int id = first + c - start;
                         if (id >= 0 && id < ITEM_CAP) { BItem it; it.off = s + 32 * c; it.cnt = len - 32 * c; it.fvs = fvs; it.nf = nf; items[id] = it; }
                     }
+                    if (tid < W) { BItem it; it.off = 0; it.cnt = 0; it.fvs = 0u; it.nf = 0; items[min(ITEM_CAP, total - start) + tid] = it; }
                     __syncthreads();
                     const int nb = min(ITEM_CAP, total - start);
-                    // each warp walks its items (w, w + W, ...) with the NEXT item's posting chunk already in flight
-                    BItem it; uint2 pk = make_uint2(0u, 0u);
-                    if (w < nb) { it = items[w]; if (lane < it.cnt) pk = __ldg(pk_lane + it.off); }
+                    // each warp walks its items (w, w + W, ...) with the NEXT item's posting chunk already in flight; W padding
+                    // items (cnt = 0, nf = 0) behind the last one keep the loop free of bounds checks
+                    BItem it = items[w]; uint2 pk = make_uint2(0u, 0u);
+                    if (lane < it.cnt) pk = __ldg(pk_lane + it.off);
                     for (int i = w; i < nb; i += W) {
-                        BItem nit; uint2 npk = make_uint2(0u, 0u);
-                        nit.off = 0; nit.cnt = 0; nit.fvs = 0u; nit.nf = 0;
-                        if (i + W < nb) { nit = items[i + W]; if (lane < nit.cnt) npk = __ldg(pk_lane + nit.off); }
+                        const BItem nit = items[i + W]; uint2 npk = make_uint2(0u, 0u);
+                        if (lane < nit.cnt) npk = __ldg(pk_lane + nit.off);
                         // idle lanes of a partial chunk add 0 to cell `lane` of each row (distinct banks; no predicates in the loop);
                         // active lanes add mulhi(v_i, w_i) + 1, so that every common term registers (sum > 0)
                         const bool on = lane < it.cnt;
@@ -410,21 +424,18 @@ __global__ void __launch_bounds__(BF * 32) spcos_block_kernel(const BlockParams 
                         const unsigned hi = P16 && jl >= (unsigned)TW ? 16u : 0u;                  // upper half-word: to-rows tile/2 ..
                         const unsigned cell = acc_s + ((P16 ? (hi ? jl - (unsigned)TW : jl) : jl) << 2);
                         const uint2 *fv = reinterpret_cast<const uint2 *>(fvtab) + it.fvs;
-                        // table entries first, updates after (ptxas keeps LDS behind an earlier ATOMS): groups of 4, then the tail
-                        int q = 0;
-                        for (; q + 4 <= it.nf; q += 4) {
-                            const uint2 e0 = fv[q], e1 = fv[q + 1], e2 = fv[q + 2], e3 = fv[q + 3];
-                            red_add_u32(cell + e0.x, (__umulhi(e0.y, wq) + one) << hi);
-                            red_add_u32(cell + e1.x, (__umulhi(e1.y, wq) + one) << hi);
-                            red_add_u32(cell + e2.x, (__umulhi(e2.y, wq) + one) << hi);
-                            red_add_u32(cell + e3.x, (__umulhi(e3.y, wq) + one) << hi);
-                        }
-                        const int r = it.nf - q;
-                        if (r > 0) {
-                            const uint2 e0 = fv[q], e1 = fv[q + (r > 1 ? 1 : 0)], e2 = fv[q + (r > 2 ? 2 : 0)];
-                            red_add_u32(cell + e0.x, (__umulhi(e0.y, wq) + one) << hi);
-                            if (r > 1) red_add_u32(cell + e1.x, (__umulhi(e1.y, wq) + one) << hi);
-                            if (r > 2) red_add_u32(cell + e2.x, (__umulhi(e2.y, wq) + one) << hi);
+                        int nf = it.nf;
+                        if (BF > 8) { while (nf > 8) { red_group<8, P16>(cell, fv, wq, one, hi); fv += 8; nf -= 8; } }
+                        switch (nf) {                             // straight-line code per row count: table entries first, updates after
+                            case 1: red_group<1, P16>(cell, fv, wq, one, hi); break;
+                            case 2: red_group<2, P16>(cell, fv, wq, one, hi); break;
+                            case 3: red_group<3, P16>(cell, fv, wq, one, hi); break;
+                            case 4: red_group<4, P16>(cell, fv, wq, one, hi); break;
+                            case 5: red_group<5, P16>(cell, fv, wq, one, hi); break;
+                            case 6: red_group<6, P16>(cell, fv, wq, one, hi); break;
+                            case 7: red_group<7, P16>(cell, fv, wq, one, hi); break;
+                            case 8: red_group<8, P16>(cell, fv, wq, one, hi); break;
+                            default: break;
                         }
                         it = nit; pk = npk;
                     }

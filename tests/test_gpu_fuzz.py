@@ -113,5 +113,5 @@ def test_string_shortcut_through_the_unmodified_orchestrator():
     m = model.get_matches()
     assert m.To.tolist() == ["Dallas Cowboys", "New York Jets"]
     assert m.Similarity.tolist() == [0.8307692307692308, 0.7692307692307692]
-    model = PolyFuzz("TF-IDF").match(["apple", "apples", "appl"], ["apple", "apples", "mouse"])
-    assert model.get_matches().Similarity.tolist() == [1.0, 1.0, 0.784]
+    model = PolyFuzz("TF-IDF").match(["apple", "apples", "appl", "recal", "house", "similarity"], ["apple", "apples", "mouse"])
+    assert model.get_matches().Similarity.tolist() == [1.0, 1.0, 0.784, 0.0, 0.588, 0.0]          # README.md:88-96, 3 decimals
