@@ -469,10 +469,8 @@ __global__ void __launch_bounds__(BF * 32, BF == 8 ? 4 : 2) spcos_block_kernel(c
                     if (kth > MQ) gate = max(gate, kth - MQ);
                 }
                 const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                for (int c0 = 0; c0 < (TW >> 2); c0 += 32) {
-                    const int c = c0 + lane;
-                    const uint4 v = rowp[c]; rowp[c] = z;
-                    if (!__any_sync(FULL, wmax(v) > gate)) continue;
+                // candidates of one 16-byte group (4 words): queue them and keep the K largest sums for the threshold
+                auto extract = [&](const uint4 &v, int c) {
 #pragma unroll
                     for (int comp = 0; comp < (P16 ? 8 : 4); ++comp) {
                         const unsigned word = (comp & 3) == 0 ? v.x : (comp & 3) == 1 ? v.y : (comp & 3) == 2 ? v.z : v.w;
@@ -483,7 +481,6 @@ __global__ void __launch_bounds__(BF * 32, BF == 8 ? 4 : 2) spcos_block_kernel(c
                         if (ncand + 32 > BLK_QCAP) drain();                 // (rare: > 224 contenders of one row inside one block)
                         if (take) cand[ncand + __popc(tm & lt)] = tau * T + c * 4 + (comp & 3) + (comp >= 4 ? TW : 0);
                         ncand += __popc(tm);
-                        // the K largest sums so far -> filter threshold
                         while (tm) {
                             const int src = __ffs(tm) - 1; tm &= tm - 1;
                             const unsigned cx = __shfl_sync(FULL, x, src);
@@ -496,6 +493,16 @@ __global__ void __launch_bounds__(BF * 32, BF == 8 ? 4 : 2) spcos_block_kernel(c
                         if (akth > MQ) gate = max(gate, akth - MQ);
                         __syncwarp();
                     }
+                };
+                const int ng = TW >> 2;                                // 16-byte groups of the row
+                for (int c0 = 0; c0 < ng; c0 += 64) {                   // two groups per lane and vote
+                    const int c = c0 + lane, c2 = c + 32;
+                    const uint4 v0 = rowp[c]; rowp[c] = z;
+                    uint4 v1 = z;
+                    if (c2 < ng) { v1 = rowp[c2]; rowp[c2] = z; }
+                    if (!__any_sync(FULL, max(wmax(v0), wmax(v1)) > gate)) continue;
+                    if (__any_sync(FULL, wmax(v0) > gate)) extract(v0, c);
+                    if (__any_sync(FULL, wmax(v1) > gate)) extract(v1, c2);
                 }
             }
             __syncthreads();
