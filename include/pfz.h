@@ -170,8 +170,9 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
  * that contains the term; 32-bit fixed-point sums in shared memory (red.shared.add.u32) filter, flagged cells are re-scored
  * exactly from the two CSR rows (as PFZ_K2_DENSE32): indices and scores are bit-identical to the other variants.  Same
  * reference call site (polyfuzz/models/_utils.py:82).
- *   post_pk: uint2[nnz] = {tile-local row, round(weight * 2^26)} in segment order (pfz_index_pack_q26 of an index built with
- *            PFZ_INDEX_BANK_ORDER32); tile: multiple of 128; k <= 32; from-rows <= 128 terms each (*err_flag_dev is set to 1
+ *   post_pk: uint2[nnz] in segment order of an index built with PFZ_INDEX_BANK_ORDER32: acc_bits 32: {tile-local row,
+ *            round(weight * 2^26)} (pfz_index_pack_q26); acc_bits 16: {accumulator word byte offset | half-word selector << 16,
+ *            max(1, round(weight * 2^15))} (pfz_index_pack_q15 with the same tile); tile: multiple of 128; k <= 32; from-rows <= 128 terms each (*err_flag_dev is set to 1
  *            otherwise); n_from < 2^22.
  *   acc_bits: 32 (one fixed-point accumulator per word, unit 2^-26) or 16 (two per word, unit 2^-15: twice the tile in the same
  *            shared memory, coarser filter; tile must be a multiple of 256).
@@ -179,6 +180,7 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
  *   Output as pfz_spcos_topk: [n_splits][n_from][k] partial lists (pfz_topk_merge when n_splits > 1).                    */
 int64_t pfz_spcos_block_ws_bytes(int32_t n_from, int64_t nnz_cap_from, int32_t n_vocab, int32_t n_splits);
 int pfz_index_pack_q26(const uint16_t *post_idx, const double *post_val, const int32_t *nnz_dev, void *post_pk, void *stream);
+int pfz_index_pack_q15(const uint16_t *post_idx, const double *post_val, const int32_t *nnz_dev, int32_t tile, void *post_pk, void *stream);
 int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from, int64_t nnz_cap_from,
                          const int32_t *seg, const void *post_pk, const int32_t *b_indptr, const int32_t *b_indices, const double *b_data,
                          int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to, int32_t k, double min_similarity, int32_t self_match,

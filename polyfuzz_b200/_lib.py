@@ -34,6 +34,7 @@ _PROTOS = {
                             c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pfz_spcos_block_ws_bytes": [c_i32, c_i64, c_i32, c_i32],
     "pfz_index_pack_q26": [c_vp, c_vp, c_vp, c_vp, c_vp],
+    "pfz_index_pack_q15": [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp],
     "pfz_spcos_topk_block": [c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f64, c_i32,
                              c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pfz_lev_pack": [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) blk_table_kernel(const int32_t *__restric
                                                         int32_t *__restrict__ blk_fvdesc, uint2 *__restrict__ blk_fv, BlockDesc *__restrict__ descs,
                                                         int n_groups, int32_t *__restrict__ err_flag) {
     constexpr int FV_CAP = BF * 64;
-    constexpr int WPB = BF == 8 ? 4 : 2;
+    constexpr int WPB = BF == 16 ? 2 : 4;
     __shared__ uint32_t s_key[WPB][FV_CAP];
     __shared__ uint32_t s_val[WPB][FV_CAP];
     const int lane = lane_id(), w = threadIdx.x >> 5;
@@ -177,6 +177,20 @@ __global__ void blk_pack_kernel(const uint16_t *__restrict__ post_idx, const dou
     const int64_t n = *nnz_ptr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         post_pk[i] = make_uint2((uint32_t)post_idx[i], (uint32_t)__double2ll_rn(post_val[i] * 67108864.0));
+}
+
+// 16-bit mode: the posting already carries what the update needs -- x = byte offset of the accumulator WORD of the to-row
+// (to-rows j and j + tile/2 share word j) | byte selector << 16 (0x4432: lower half-word, 0x3244: upper), y = w15 =
+// max(1, round(weight * 2^15))
+__global__ void blk_pack15_kernel(const uint16_t *__restrict__ post_idx, const double *__restrict__ post_val, const int32_t *__restrict__ nnz_ptr,
+                                  int half_tile, uint2 *__restrict__ post_pk) {
+    const int64_t n = *nnz_ptr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t j = post_idx[i];
+        const bool hi = j >= (uint32_t)half_tile;
+        const uint32_t w15 = (uint32_t)max(1ll, __double2ll_rn(post_val[i] * 32768.0));
+        post_pk[i] = make_uint2(((hi ? j - (uint32_t)half_tile : j) << 2) | ((hi ? 0x3244u : 0x4432u) << 16), w15);
+    }
 }
 
 // ---- main kernel -----------------------------------------------------------------------------------------------
@@ -519,6 +533,502 @@ __global__ void __launch_bounds__(BF * 32, BF == 8 ? 4 : 2) spcos_block_kernel(c
     }
 }
 
+// ---- main kernel, version 3 ------------------------------------------------------------------------------------
+// Same algorithm as spcos_block_kernel (fixed-point red.shared accumulators shared by the CTA, filter + exact re-scoring), laid
+// out for instruction count and registers after the ncu profile of version 2 (profiles/k2_r02_block_v2_metrics.txt: 67 warp
+// instructions per work item, 43 per 256 scanned cells, local-memory spills in both loops, 5 barriers per (block, tile) unit):
+//   * everything rare -- queueing candidates, maintaining the K largest sums, exact re-scoring, the top-k list -- lives in
+//     NOINLINE functions whose state is in shared memory (B3Row), so the two hot loops (work items, scan) keep a handful of
+//     registers and nothing spills;
+//   * work items are allocated with one shared-memory atomic per warp (no block-wide scan), the segment offsets of the next tile
+//     are prefetched during the current one, and a unit needs 2 barriers: [table | A | items (red) | B | scan of the own row];
+//     the scan of tile t overlaps the table phase of tile t+1 (barrier A of t+1 is the one that protects the accumulators);
+//   * idle lanes of a partial chunk add into 32 dump words behind their row's cells (ptxas does not predicate ATOMS: a
+//     predicated red costs a divergent branch; a dump cell costs one select per item);
+//   * the item loop keeps B3_DEPTH posting chunks in flight per warp;
+//   * 16-bit mode: update = ceil(v16 * w15 / 2^16) placed in its half-word by one byte permute (IMAD + PRMT), v16 =
+//     max(1, floor(v * 2^16)), w15 = max(1, round(w * 2^15)) pre-packed with the word offset and the permute selector
+//     (pfz_index_pack_q15): -1.01 < update - v*w*2^15 < 2.01 units per product, >= 1 for every common term; margin 4 m + 2.
+constexpr int B3_ICAP_PER_ROW = 64;              // staged work items per unit = 64 x block rows; larger units walk the term table directly
+constexpr int B3_QCAP = 128;                     // candidates a from-row may queue before they are re-scored exactly
+constexpr int B3_DEPTH = 3;                      // posting chunks in flight per warp
+
+struct __align__(16) B3Item { int off; int cnt; unsigned fva; int nf; };
+// what the rare paths need of the kernel parameters (one copy per CTA in shared memory)
+struct __align__(16) B3Ctx {
+    const int32_t *a_indptr; const int32_t *a_indices; const double *a_data;
+    const int32_t *b_indptr; const int32_t *b_indices; const double *b_data;
+    int64_t to_base; double scale; int K; int T; int TW; int pad;
+};
+// filter / top-k state of one from-row (= one warp)
+struct __align__(16) B3Row {
+    double tv[32]; int ti[32];                   // exact top-k list, lane r = rank r
+    unsigned av[32];                             // the K largest fixed-point sums seen (lane r = r-th largest)
+    int cand[B3_QCAP];                           // queued candidates (local to-row ids)
+    int row, self_loc, ncand; unsigned thr, akth, MQ, gate; int pad;
+};
+
+// exact scoring + insertion of the queued candidates of one from-row (32 per round, newest first); raises thr to the K-th exact key
+__device__ __noinline__ void blk3_drain(const B3Ctx *cx, B3Row *rs) {
+    const int lane = threadIdx.x & 31;
+    const int K = cx->K, row = rs->row, self_loc = rs->self_loc;
+    const int32_t *__restrict__ b_indptr = cx->b_indptr;
+    const int a0 = cx->a_indptr[row], m = cx->a_indptr[row + 1] - a0;
+    int ncand = rs->ncand;
+    double tv = rs->tv[lane]; int ti = rs->ti[lane];
+    double kv = shfl_d(tv, K - 1); int ki = __shfl_sync(FULL, ti, K - 1);
+    while (ncand > 0) {
+        const int n_round = min(32, ncand), off = ncand - n_round;
+        double sc = 0.0; int j = -1; bool cnd = false;
+        if (lane < n_round) {
+            const int jloc = rs->cand[off + lane];
+            const int b0 = b_indptr[jloc];
+            sc = blk_exact_dot(cx->a_indices + a0, cx->a_data + a0, m, cx->b_indices + b0, cx->b_data + b0, b_indptr[jloc + 1] - b0);
+            j = (int)(cx->to_base + jloc);
+            cnd = blk_key_before(sc, j, kv, ki) && jloc != self_loc;
+        }
+        unsigned cm = __ballot_sync(FULL, cnd);
+        while (cm) {
+            const int src = __ffs(cm) - 1;
+            const double cs = shfl_d(sc, src);
+            const int cj = __shfl_sync(FULL, j, src);
+            const bool stays = (lane < K) && blk_key_before(tv, ti, cs, cj);
+            const int pos = __popc(__ballot_sync(FULL, stays));
+            const double uv = __shfl_up_sync(FULL, tv, 1);
+            const int ui = __shfl_up_sync(FULL, ti, 1);
+            if (lane > pos) { tv = uv; ti = ui; }
+            else if (lane == pos) { tv = cs; ti = cj; }
+            kv = shfl_d(tv, K - 1);
+            ki = __shfl_sync(FULL, ti, K - 1);
+            cnd = cnd && lane != src && blk_key_before(sc, j, kv, ki);
+            cm = __ballot_sync(FULL, cnd);
+        }
+        ncand = off;
+    }
+    rs->tv[lane] = tv; rs->ti[lane] = ti;
+    if (lane == 0) {
+        rs->ncand = 0;
+        if (ki >= 0) {
+            const double y = kv * cx->scale - (double)rs->MQ;
+            const unsigned t = y <= 0.0 ? 0u : (unsigned)__double2ll_rd(y);
+            if (t > rs->thr) rs->thr = t;
+        }
+    }
+    __syncwarp();
+}
+
+// largest accumulator of a 16-byte group: plain maximum, or the maximum over the 16-bit halves
+template <bool P16>
+__device__ __forceinline__ unsigned blk3_wmax(const uint4 &v) {
+    if (!P16) return max(max(v.x, v.y), max(v.z, v.w));
+    const unsigned m2 = __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w));
+    return max(m2 & 0xffffu, m2 >> 16);
+}
+
+__device__ __forceinline__ uint4 lds128(unsigned a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128_zero(unsigned a) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" :: "r"(a), "r"(0u));
+}
+// Fewer than K sums seen so far: the K-th largest of the 32 lane maxima of the row bounds the unit's K-th best sum from below.
+// Returns the gate for this scan.  row_s: shared-memory address of the row's cells.
+template <bool P16>
+__device__ __noinline__ unsigned blk3_first_gate(const B3Ctx *cx, const B3Row *rs, unsigned row_s) {
+    const int lane = threadIdx.x & 31;
+    const int ng = cx->TW >> 2;
+    unsigned mx = 0u;
+    for (int c = lane; c < ng; c += 32) mx = max(mx, blk3_wmax<P16>(lds128(row_s + ((unsigned)c << 4))));
+    const unsigned srt = warp_sort_desc_u32(mx, lane);
+    const unsigned kth = __shfl_sync(FULL, srt, cx->K - 1);
+    unsigned gate = rs->gate;
+    const unsigned MQ = rs->MQ;
+    if (kth > MQ) gate = max(gate, kth - MQ);
+    return gate;
+}
+
+// Candidates of one scan step (two 16-byte groups per lane: c_base + lane and c_base + 32 + lane; hl0 / hl1 = lanes whose group
+// holds a cell above the gate).  The groups are still in shared memory: for every flagged group the first lanes of the warp
+// read ONE cell each (a half-word in 16-bit mode), vote, queue the cells above the gate and keep the K largest sums; the
+// queue is re-scored exactly when it fills.  Returns the new gate.
+template <bool P16>
+__device__ __noinline__ unsigned blk3_extract(const B3Ctx *cx, B3Row *rs, unsigned row_s, int c_base, unsigned hl0, unsigned hl1, unsigned gate, int cell0) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int K = cx->K, TW = cx->TW;
+    const unsigned MQ = rs->MQ;
+    unsigned av = rs->av[lane], akth = rs->akth;
+    int ncand = rs->ncand;
+    constexpr int NC = P16 ? 8 : 4;                                 // cells per 16-byte group
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+        unsigned hl = g == 0 ? hl0 : hl1;
+#pragma unroll 1
+        while (hl) {
+            const int src = __ffs(hl) - 1; hl &= hl - 1;
+            const int grp = c_base + src + 32 * g;
+            unsigned x = 0u;
+            if (lane < NC) {
+                const unsigned a = row_s + ((unsigned)grp << 4);
+                if (P16) { unsigned short h; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a + 2u * (unsigned)lane)); x = h; }
+                else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(a + 4u * (unsigned)lane));
+            }
+            const bool take = x > gate;
+            unsigned tm = __ballot_sync(FULL, take);
+            if (tm == 0u) continue;
+            if (ncand + NC > B3_QCAP) {                               // queue full: re-score what is queued now
+                if (lane == 0) rs->ncand = ncand;
+                __syncwarp();
+                blk3_drain(cx, rs);
+                ncand = 0;
+                gate = max(gate, rs->thr);
+            }
+            if (take) rs->cand[ncand + __popc(tm & lt)] = cell0 + grp * 4 + (P16 ? (lane >> 1) + ((lane & 1) ? TW : 0) : lane);
+            ncand += __popc(tm);
+            while (tm) {
+                const int s2 = __ffs(tm) - 1; tm &= tm - 1;
+                const unsigned cx2 = __shfl_sync(FULL, x, s2);
+                if (cx2 <= akth) continue;
+                const int pos = __popc(__ballot_sync(FULL, (lane < K) && av >= cx2));
+                const unsigned up = __shfl_up_sync(FULL, av, 1);
+                if (lane > pos) av = up; else if (lane == pos) av = cx2;
+                akth = __shfl_sync(FULL, av, K - 1);
+            }
+            if (akth > MQ) gate = max(gate, akth - MQ);
+        }
+    }
+    rs->av[lane] = av;
+    if (lane == 0) { rs->akth = akth; rs->ncand = ncand; rs->gate = gate; }
+    __syncwarp();
+    return gate;
+}
+
+// one posting chunk applied to the from-rows that hold the term (nf is warp-uniform); idle lanes (pk = 0) add into their dump word.
+// 16-bit mode: pk = {word byte offset | selector << 16, w15}, update = ceil(v16 * w15 / 2^16) in its half-word (IMAD + PRMT);
+// the (row, weight) list is read two entries at a time, the odd tail masked (weight 0 adds 0).
+template <bool P16>
+__device__ __forceinline__ void blk3_process(int lane, int cnt, unsigned fva, int nf, uint2 pk, unsigned acc_s, unsigned dump_s) {
+    unsigned cell, sel = 0u;
+    const unsigned wq = pk.y;
+    if (P16) { cell = acc_s + (pk.x & 0xffffu); sel = pk.x >> 16; }
+    else cell = acc_s + (pk.x << 2);
+    if (lane >= cnt) cell = dump_s;
+    if (P16) {
+#pragma unroll 1
+        for (; nf > 0; nf -= 2, fva += 16u) {
+            uint2 e0, e1;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0.x), "=r"(e0.y) : "r"(fva));
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+8];" : "=r"(e1.x), "=r"(e1.y) : "r"(fva));
+            if (nf == 1) e1.y = 0u;                                 // (the next term's entry, or the sentinel behind the table)
+            red_add_u32(cell + e0.x, __byte_perm(e0.y * wq + 0xffffu, 0u, sel));
+            red_add_u32(cell + e1.x, __byte_perm(e1.y * wq + 0xffffu, 0u, sel));
+        }
+    } else {
+#pragma unroll 1
+        for (; nf >= 2; nf -= 2, fva += 16u) {
+            uint2 e0, e1;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0.x), "=r"(e0.y) : "r"(fva));
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+8];" : "=r"(e1.x), "=r"(e1.y) : "r"(fva));
+            red_add_u32(cell + e0.x, __umulhi(e0.y, wq) + 1u);
+            red_add_u32(cell + e1.x, __umulhi(e1.y, wq) + 1u);
+        }
+        if (nf) {
+            uint2 e0;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0.x), "=r"(e0.y) : "r"(fva));
+            red_add_u32(cell + e0.x, __umulhi(e0.y, wq) + 1u);
+        }
+    }
+}
+
+// The item phase of one unit as its own function (own register allocation): warp w walks items w, w + W, ... with the posting
+// chunks of the next B3_DEPTH items in flight.  items_s: shared address of the item array.  A slot behind the last item holds an
+// empty item (cnt = nf = 0).
+template <int W, bool P16>
+__device__ __noinline__ void blk3_item_loop(unsigned items_s, int total, const uint2 *__restrict__ pk_lane, unsigned acc_s, unsigned dump_s) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int qc[B3_DEPTH], qn[B3_DEPTH]; unsigned qa[B3_DEPTH]; uint2 qp[B3_DEPTH];
+#pragma unroll
+    for (int d = 0; d < B3_DEPTH; ++d) {
+        const int i = w + d * W;
+        qc[d] = 0; qn[d] = 0; qa[d] = 0u; qp[d] = make_uint2(0u, 0u);
+        if (i < total) {
+            const uint4 it = lds128(items_s + ((unsigned)i << 4));            // {off, cnt, fva, nf}
+            qc[d] = (int)it.y; qn[d] = (int)it.w; qa[d] = it.z;
+            if (lane < (int)it.y) qp[d] = __ldg(pk_lane + (int)it.x);
+        }
+    }
+#pragma unroll 1
+    for (int i0 = w; i0 < total; i0 += B3_DEPTH * W) {
+#pragma unroll
+        for (int d = 0; d < B3_DEPTH; ++d) {
+            blk3_process<P16>(lane, qc[d], qa[d], qn[d], qp[d], acc_s, dump_s);
+            const int ni = i0 + (d + B3_DEPTH) * W;
+            qc[d] = 0; qn[d] = 0; qp[d] = make_uint2(0u, 0u);
+            if (ni < total) {
+                const uint4 it = lds128(items_s + ((unsigned)ni << 4));
+                qc[d] = (int)it.y; qn[d] = (int)it.w; qa[d] = it.z;
+                if (lane < (int)it.y) qp[d] = __ldg(pk_lane + (int)it.x);
+            }
+        }
+    }
+}
+
+// Scan + clear of one row.  The hot loop is a LEAF function (a call inside a loop makes ptxas keep the loop state in local
+// memory): it clears 16-byte groups (two per lane and step) until one holds a cell above the gate, which it leaves in place
+// and reports; the caller hands that step to blk3_extract and resumes.
+template <bool P16>
+__device__ __noinline__ int blk3_scan_until_hit(unsigned row_s, int c, int ng, unsigned gate) {
+#pragma unroll 1
+    for (; c < ng; c += 64) {
+        const unsigned a = row_s + ((unsigned)c << 4);
+        const bool two = c + 32 < ng;
+        const uint4 v0 = lds128(a);
+        uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
+        if (two) v1 = lds128(a + 512u);
+        if (__any_sync(FULL, max(blk3_wmax<P16>(v0), blk3_wmax<P16>(v1)) > gate)) break;
+        sts128_zero(a);
+        if (two) sts128_zero(a + 512u);
+    }
+    return c;
+}
+// The rest of a row scan once a step holds a cell above the gate (or while fewer than K sums have been seen: first != 0).
+template <bool P16>
+__device__ __noinline__ void blk3_scan_slow(const B3Ctx *cx, B3Row *rs, unsigned row_s, int cell0, int c, int first) {
+    const int lane = threadIdx.x & 31;
+    const int ng = cx->TW >> 2;                                    // 16-byte groups of the row (a multiple of 32)
+    unsigned gate = rs->gate;
+    if (first) {
+        gate = blk3_first_gate<P16>(cx, rs, row_s);
+        c = blk3_scan_until_hit<P16>(row_s, lane, ng, gate);
+    }
+    while (c < ng) {
+        const unsigned a = row_s + ((unsigned)c << 4);
+        const bool two = c + 32 < ng;
+        const uint4 v0 = lds128(a);
+        uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
+        if (two) v1 = lds128(a + 512u);
+        const unsigned hl0 = __ballot_sync(FULL, blk3_wmax<P16>(v0) > gate), hl1 = __ballot_sync(FULL, blk3_wmax<P16>(v1) > gate);
+        gate = blk3_extract<P16>(cx, rs, row_s, c - lane, hl0, hl1, gate, cell0);
+        sts128_zero(a);
+        if (two) sts128_zero(a + 512u);
+        c = blk3_scan_until_hit<P16>(row_s, c + 64, ng, gate);
+    }
+    if (lane == 0) rs->gate = gate;
+    __syncwarp();
+}
+
+template <int BF, bool P16>
+__host__ __device__ inline size_t blk3_arena_bytes(int T) {
+    return (size_t)BF * (T * (P16 ? 2 : 4) + 128)   // acc: per from-row the tile's cells + 32 dump words (idle lanes)
+           + (size_t)BF * B3_ICAP_PER_ROW * 16 // items
+           + (size_t)(BF * 64 + 2) * 8         // fv (+ sentinel)
+           + (size_t)BF * sizeof(B3Row)        // per-row filter / top-k state
+           + sizeof(B3Ctx) + 64;               // context, counters
+}
+
+template <int BF, bool P16>
+__global__ void __launch_bounds__(BF * 32, 32 / BF) spcos_blk3_kernel(const BlockParams P) {
+    constexpr int W = BF, NT = BF * 32, FV_CAP = BF * 64, B3_ICAP = BF * B3_ICAP_PER_ROW;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int T = P.tile;
+    const int TW = P16 ? (T >> 1) : T;                                 // 32-bit accumulator words per from-row
+    const int RW = TW + 32;                                            // row stride in words: cells + 32 dump words
+    unsigned *acc = reinterpret_cast<unsigned *>(dyn);
+    B3Item *items = reinterpret_cast<B3Item *>(dyn + (size_t)BF * RW * 4);
+    uint2 *fvtab = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(items) + (size_t)B3_ICAP * 16);
+    B3Row *rs = reinterpret_cast<B3Row *>(reinterpret_cast<unsigned char *>(fvtab) + (size_t)(FV_CAP + 2) * 8) + w;
+    B3Ctx *cx = reinterpret_cast<B3Ctx *>(reinterpret_cast<unsigned char *>(fvtab) + (size_t)(FV_CAP + 2) * 8 + (size_t)BF * sizeof(B3Row));
+    int *misc = reinterpret_cast<int *>(cx + 1);
+    int *icnt = misc;                                                   // [2] item counters (tile parity)
+    int *bcast = misc + 2;
+    int *wsum = misc + 4;                                               // [W <= 12]
+
+    for (int q = tid; q < BF * RW; q += NT) acc[q] = 0u;
+    if (tid < 4) misc[tid] = 0;
+    if (tid == 0) {
+        cx->a_indptr = P.a_indptr; cx->a_indices = P.a_indices; cx->a_data = P.a_data;
+        cx->b_indptr = P.b_indptr; cx->b_indices = P.b_indices; cx->b_data = P.b_data;
+        cx->to_base = P.to_base; cx->scale = P16 ? 32768.0 : K2B_SCALE; cx->K = P.k; cx->T = T; cx->TW = TW; cx->pad = 0;
+    }
+    const unsigned acc_s = sm_u32(acc);
+    const unsigned dump_s = acc_s + ((unsigned)(TW + lane) << 2);       // this lane's dump word of row 0
+    const unsigned fv_s = sm_u32(fvtab);
+    const unsigned items_s = sm_u32(items);
+    const uint2 *pk_lane = P.post_pk + lane;
+    const int32_t *__restrict__ seg = P.seg;
+    const int n_tiles = P.n_tiles;
+    const int split = blockIdx.y;
+    const int tiles_per = (P.n_tiles + P.n_splits - 1) / P.n_splits;
+    const int tau_lo = split * tiles_per;
+    const int tau_hi = min(P.n_tiles, tau_lo + tiles_per);
+    int32_t *counter = P.counter + split;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) { bcast[0] = atomicAdd(counter, 1); icnt[0] = 0; icnt[1] = 0; }
+        __syncthreads();
+        const int di = bcast[0];
+        __syncthreads();
+        if (di >= P.n_desc) break;
+        const BlockDesc D = P.descs[di];
+        const int nrows = D.nrows, nterms = D.nterms;
+        if (nrows == 0) continue;
+        // warp w owns from-row w of the block
+        const bool has_row = w < nrows;
+        int stau = -1;
+        {
+            int row = 0, m = 0, sjl = 0;
+            if (has_row) {
+                row = P.perm[D.pos0 + w];
+                m = P.a_indptr[row + 1] - P.a_indptr[row];
+                const int64_t self_j = P.from_base + row - P.to_base;       // local to-row of the diagonal
+                if (P.self_match && self_j >= 0 && self_j < (int64_t)P.n_to) { stau = (int)(self_j / T); sjl = (int)(self_j - (int64_t)stau * T); }
+            }
+            rs->tv[lane] = P.min_sim; rs->ti[lane] = -1; rs->av[lane] = 0u;
+            if (lane == 0) {
+                const unsigned MQ = P16 ? (unsigned)(4 * m + 2) : K2B_MARGIN_Q;  // filter margin in accumulator units (16-bit: -1.01 < update - exact < 2.01)
+                const double y = fmax(P.min_sim, 0.0) * (P16 ? 32768.0 : K2B_SCALE) - (double)MQ;
+                const unsigned thr = y <= 0.0 ? 0u : (unsigned)__double2ll_rd(y);
+                rs->row = row; rs->self_loc = stau >= 0 ? stau * T + sjl : -1; rs->ncand = 0;
+                rs->thr = thr; rs->akth = 0u; rs->MQ = MQ; rs->gate = thr;
+                wsum[w] = m;
+            }
+        }
+        // this thread's term (terms are dealt round-robin to the warps; first NT terms of the block, a block rarely has more):
+        // segment row and (row, weight) list
+        const int u_my = lane * W + w;
+        int my_seg = 0; unsigned my_fva = 0u; int my_nf = 0;
+        int pf_s = 0, pf_e = 0;
+        if (u_my < nterms) {
+            my_seg = P.blk_terms[D.base + u_my] * n_tiles;
+            const unsigned fvd = (unsigned)P.blk_fvdesc[D.base + u_my];
+            my_fva = fv_s + ((fvd >> 5) << 3); my_nf = (int)(fvd & 31u);
+            pf_s = seg[my_seg + tau_lo]; pf_e = seg[my_seg + tau_lo + 1];
+        }
+        __syncthreads();
+        {
+            int nfv_total = 0;
+#pragma unroll
+            for (int q = 0; q < W; ++q) nfv_total += wsum[q];
+            for (int e = tid; e <= nfv_total; e += NT) {
+                uint2 x = make_uint2(0u, 0u);                           // (sentinel behind the table: the masked odd tail reads it)
+                if (e < nfv_total) {
+                    x = P.blk_fv[D.base + e];
+                    if (P16) x.y = max(1u, x.y >> 16);                  // v16 = max(1, floor(v * 2^16))
+                }
+                fvtab[e] = x;
+            }
+        }
+        // (the first barrier A below publishes fvtab and the row states)
+
+        for (int tau = tau_lo; tau < tau_hi; ++tau) {
+            const int par = tau & 1;
+            // ---- table phase: one work item per 32 postings of a (term, tile) segment ----
+            auto emit = [&](int s, int len, unsigned fva, int nf) {
+                const int nch = (len + 31) >> 5;
+                const int incl = warp_incl_scan(nch);
+                int first = 0;
+                if (lane == 31 && incl > 0) first = atomicAdd(&icnt[par], incl);
+                first = __shfl_sync(FULL, first, 31) + incl - nch;
+                if (nch > 0 && first < B3_ICAP) { B3Item it; it.off = s; it.cnt = len; it.fva = fva; it.nf = nf; items[first] = it; }
+                unsigned big = __ballot_sync(FULL, nch > 1);
+                while (big) {                                             // the further chunks of long segments: written by the whole warp
+                    const int src = __ffs(big) - 1; big &= big - 1;
+                    const int s2 = __shfl_sync(FULL, s, src), l2 = __shfl_sync(FULL, len, src), f2 = __shfl_sync(FULL, first, src);
+                    const unsigned a2 = __shfl_sync(FULL, fva, src); const int n2 = __shfl_sync(FULL, nf, src);
+                    for (int c = 1 + lane; c < ((l2 + 31) >> 5); c += 32)
+                        if (f2 + c < B3_ICAP) { B3Item it; it.off = s2 + 32 * c; it.cnt = l2 - 32 * c; it.fva = a2; it.nf = n2; items[f2 + c] = it; }
+                }
+            };
+            if (w < nterms) {                                             // (warp-uniform: lane 0 holds term w)
+                const int s = pf_s, len = pf_e - pf_s;
+                if (u_my < nterms && tau + 1 < tau_hi) { pf_s = seg[my_seg + tau + 1]; pf_e = seg[my_seg + tau + 2]; }
+                emit(s, u_my < nterms ? len : 0, my_fva, my_nf);
+            }
+            for (int tb = NT; tb < nterms; tb += NT) {                    // blocks with more than NT distinct terms (rare)
+                if (tb + (w << 5) < nterms) {
+                    const int u = tb + tid;
+                    int s = 0, len = 0; unsigned fva = 0u; int nf = 0;
+                    if (u < nterms) {
+                        const int sb = P.blk_terms[D.base + u] * n_tiles + tau;
+                        const unsigned fvd = (unsigned)P.blk_fvdesc[D.base + u];
+                        s = seg[sb]; len = seg[sb + 1] - s; fva = fv_s + ((fvd >> 5) << 3); nf = (int)(fvd & 31u);
+                    }
+                    emit(s, len, fva, nf);
+                }
+            }
+            __syncthreads();                                              // ---- barrier A: items visible; every row of the previous tile scanned
+            const int total = icnt[par];
+            if (tid == 0) icnt[par ^ 1] = 0;
+            if (total == 0) { __syncthreads(); continue; }                 // (uniform; the barrier orders the counter reset)
+
+            if (total <= B3_ICAP) {
+                blk3_item_loop<W, P16>(items_s, total, pk_lane, acc_s, dump_s);
+            } else {
+                // oversized unit: warps walk the term table directly (terms w, w + W, ...), chunk by chunk
+                for (int u = w; u < nterms; u += W) {
+                    const int sb = P.blk_terms[D.base + u] * n_tiles + tau;
+                    const unsigned fvd = (unsigned)P.blk_fvdesc[D.base + u];
+                    const int s = seg[sb], len = seg[sb + 1] - s;
+                    for (int c = 0; c < len; c += 32) {
+                        uint2 pk = make_uint2(0u, 0u);
+                        if (lane < len - c) pk = __ldg(pk_lane + s + c);
+                        blk3_process<P16>(lane, len - c, fv_s + ((fvd >> 5) << 3), (int)(fvd & 31u), pk, acc_s, dump_s);
+                    }
+                }
+            }
+            __syncthreads();                                              // ---- barrier B: every update of the unit done
+            // ---- scan + clear: warp w scans the accumulators of its row against the row's threshold ----
+            if (has_row) {
+                if (stau == tau) {                                     // the diagonal never competes
+                    if (lane == 0) {
+                        const int sjl = rs->self_loc - stau * T;
+                        if (P16) acc[(size_t)w * RW + (sjl >= TW ? sjl - TW : sjl)] &= (sjl >= TW ? 0x0000ffffu : 0xffff0000u);
+                        else acc[(size_t)w * RW + sjl] = 0u;
+                    }
+                    __syncwarp();
+                }
+                const unsigned row_s = acc_s + (unsigned)(w * RW) * 4u;
+                if (rs->akth == 0u) blk3_scan_slow<P16>(cx, rs, row_s, tau * T, 0, 1);
+                else {
+                    const int c = blk3_scan_until_hit<P16>(row_s, lane, TW >> 2, rs->gate);
+                    if (c < (TW >> 2)) blk3_scan_slow<P16>(cx, rs, row_s, tau * T, c, 0);
+                }
+            }
+        }
+        if (has_row) {
+            __syncwarp();
+            blk3_drain(cx, rs);
+            if (lane < P.k) {
+                const size_t o = ((size_t)split * P.n_from + rs->row) * P.k + lane;
+                const int ti = rs->ti[lane];
+                P.top_idx[o] = ti;
+                P.top_val[o] = (ti >= 0) ? rs->tv[lane] : 0.0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int BF, bool P16>
+static int launch_blk3(const BlockParams &P, int n_groups, int sms, int smem_max, cudaStream_t st) {
+    const size_t arena = (blk3_arena_bytes<BF, P16>(P.tile) + 15) & ~(size_t)15;
+    PFZ_REQUIRE(arena <= (size_t)smem_max, "pfz_spcos_topk_block: tile %d x %d rows needs %zu B shared memory > %d available", P.tile, BF, arena, smem_max);
+    PFZ_CUDA_OK(cudaFuncSetAttribute(spcos_blk3_kernel<BF, P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)arena));
+    int occ = 0;
+    PFZ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spcos_blk3_kernel<BF, P16>, BF * 32, arena));
+    if (occ < 1) occ = 1;
+    int gx = sms * occ;
+    if (gx > 2 * n_groups) gx = 2 * n_groups;
+    if (P.n_splits > 1) { gx = (gx + P.n_splits - 1) / P.n_splits; if (gx < 1) gx = 1; }
+    spcos_blk3_kernel<BF, P16><<<dim3(gx, P.n_splits), BF * 32, arena, st>>>(P);
+    PFZ_LAUNCH_OK();
+    return 0;
+}
+
 static int blk_grid(int64_t work, int threads, int cap) {
     int64_t g = (work + threads - 1) / threads;
     if (g < 1) g = 1;
@@ -534,7 +1044,7 @@ struct BlockWs {
 static BlockWs block_ws_layout(int64_t n_from, int64_t nnz_cap, int64_t n_vocab, int n_splits) {
     BlockWs L; size_t o = 0;
     const int64_t vp = pow2_at_least(n_vocab), np = pow2_at_least(n_from);
-    const int64_t n_groups = (n_from + 7) / 8;                      // enough for either block size
+    const int64_t n_groups = (n_from + 3) / 4;                      // enough for every block size
     L.term_keys = o; o += align256((size_t)vp * 8);
     L.term_rank = o; o += align256((size_t)(n_vocab + 1) * 4);
     L.row_keys = o; o += align256((size_t)np * 8);
@@ -582,6 +1092,13 @@ int pfz_index_pack_q26(const uint16_t *post_idx, const double *post_val, const i
     return 0;
 }
 
+int pfz_index_pack_q15(const uint16_t *post_idx, const double *post_val, const int32_t *nnz_dev, int32_t tile, void *post_pk, void *stream) {
+    PFZ_REQUIRE(tile >= 256 && tile <= 8192 && (tile % 256) == 0, "pfz_index_pack_q15: tile %d must be a multiple of 256 in 256..8192", tile);
+    blk_pack15_kernel<<<148 * 8, 256, 0, as_stream(stream)>>>(post_idx, post_val, nnz_dev, tile / 2, reinterpret_cast<uint2 *>(post_pk));
+    PFZ_LAUNCH_OK();
+    return 0;
+}
+
 int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from, int64_t nnz_cap_from,
                          const int32_t *seg, const void *post_pk, const int32_t *b_indptr, const int32_t *b_indices, const double *b_data,
                          int32_t n_vocab, int32_t tile, int32_t n_tiles, int32_t n_to, int32_t k, double min_similarity, int32_t self_match,
@@ -589,7 +1106,7 @@ int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, cons
                          double *top_val, int32_t *err_flag_dev, void *ws, void *stream) {
     PFZ_REQUIRE(k >= 1 && k <= 32, "pfz_spcos_topk_block: k=%d unsupported (1..32)", k);
     PFZ_REQUIRE(tile >= 128 && tile <= 4096 && (tile % 128) == 0, "pfz_spcos_topk_block: tile %d must be a multiple of 128 in 128..4096", tile);
-    PFZ_REQUIRE(block_rows == 8 || block_rows == 16, "pfz_spcos_topk_block: block_rows %d must be 8 or 16", block_rows);
+    PFZ_REQUIRE(block_rows == 4 || block_rows == 8 || block_rows == 16, "pfz_spcos_topk_block: block_rows %d must be 4, 8 or 16", block_rows);
     PFZ_REQUIRE(acc_bits == 32 || (acc_bits == 16 && tile % 256 == 0), "pfz_spcos_topk_block: acc_bits %d must be 32, or 16 with a tile that is a multiple of 256", acc_bits);
     PFZ_REQUIRE(n_splits >= 1 && n_splits <= n_tiles, "pfz_spcos_topk_block: n_splits %d out of range", n_splits);
     PFZ_REQUIRE(n_from < (1 << 22), "pfz_spcos_topk_block: n_from %d exceeds the 22-bit row id of the clustering key", n_from);
@@ -626,18 +1143,30 @@ int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, cons
     blk_perm_kernel<<<blk_grid(n_from + 1, 256, 148 * 16), 256, 0, st>>>(row_keys, a_indptr, n_from, perm, pos_ptr);
     PFZ_LAUNCH_OK();
     if (scan_exclusive_i32(pos_ptr, pos_ptr, (int64_t)n_from + 1, w + L.scan_ws, st)) return 1;
-    if (block_rows == 8)
-        blk_table_kernel<8><<<blk_grid((int64_t)n_groups * 32, 128, 148 * 16), 128, 0, st>>>(a_indptr, a_indices, a_data, n_from, perm, pos_ptr, tile * (acc_bits == 16 ? 2 : 4),
+    const char *env_v = getenv("PFZ_BLOCK_KERNEL");                // developer knob: 2 = the previous main kernel (kept for A/B runs)
+    const bool v2 = env_v && atoi(env_v) == 2;
+    const int row_stride = tile * (acc_bits == 16 ? 2 : 4) + (v2 ? 0 : 128);   // version 3: 32 dump words behind every row
+    if (block_rows == 4)
+        blk_table_kernel<4><<<blk_grid((int64_t)n_groups * 32, 128, 148 * 16), 128, 0, st>>>(a_indptr, a_indices, a_data, n_from, perm, pos_ptr, row_stride,
+                                                                                             blk_terms, blk_fvdesc, blk_fv, descs, n_groups, err_flag_dev);
+    else if (block_rows == 8)
+        blk_table_kernel<8><<<blk_grid((int64_t)n_groups * 32, 128, 148 * 16), 128, 0, st>>>(a_indptr, a_indices, a_data, n_from, perm, pos_ptr, row_stride,
                                                                                              blk_terms, blk_fvdesc, blk_fv, descs, n_groups, err_flag_dev);
     else
-        blk_table_kernel<16><<<blk_grid((int64_t)n_groups * 32, 64, 148 * 16), 128, 0, st>>>(a_indptr, a_indices, a_data, n_from, perm, pos_ptr, tile * (acc_bits == 16 ? 2 : 4),
+        blk_table_kernel<16><<<blk_grid((int64_t)n_groups * 32, 64, 148 * 16), 128, 0, st>>>(a_indptr, a_indices, a_data, n_from, perm, pos_ptr, row_stride,
                                                                                               blk_terms, blk_fvdesc, blk_fv, descs, n_groups, err_flag_dev);
     PFZ_LAUNCH_OK();
     PFZ_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t) * (size_t)n_splits, st));
     BlockParams P{a_indptr, a_indices, a_data, n_from, perm, descs, 2 * n_groups, blk_terms, blk_fvdesc, blk_fv, seg,
                   reinterpret_cast<const uint2 *>(post_pk), b_indptr, b_indices, b_data, tile, n_tiles, n_to, k, min_similarity, self_match,
                   from_index_base, to_index_base, n_splits, top_idx, top_val, counters};
-    if (acc_bits == 16) return block_rows == 8 ? launch_block<8, true>(P, n_groups, sms, smem_max, st) : launch_block<16, true>(P, n_groups, sms, smem_max, st);
-    return block_rows == 8 ? launch_block<8, false>(P, n_groups, sms, smem_max, st) : launch_block<16, false>(P, n_groups, sms, smem_max, st);
+    if (v2) {
+        PFZ_REQUIRE(block_rows != 4 && acc_bits == 32, "pfz_spcos_topk_block: the version-2 kernel has no 4-row variant and reads the q26 posting format");
+        if (acc_bits == 16) return block_rows == 8 ? launch_block<8, true>(P, n_groups, sms, smem_max, st) : launch_block<16, true>(P, n_groups, sms, smem_max, st);
+        return block_rows == 8 ? launch_block<8, false>(P, n_groups, sms, smem_max, st) : launch_block<16, false>(P, n_groups, sms, smem_max, st);
+    }
+    if (block_rows == 4) return acc_bits == 16 ? launch_blk3<4, true>(P, n_groups, sms, smem_max, st) : launch_blk3<4, false>(P, n_groups, sms, smem_max, st);
+    if (acc_bits == 16) return block_rows == 8 ? launch_blk3<8, true>(P, n_groups, sms, smem_max, st) : launch_blk3<16, true>(P, n_groups, sms, smem_max, st);
+    return block_rows == 8 ? launch_blk3<8, false>(P, n_groups, sms, smem_max, st) : launch_blk3<16, false>(P, n_groups, sms, smem_max, st);
 }
 }

@@ -419,11 +419,11 @@ class NgramTfidf:
 # to-tile rows per K2 variant: the list kernel wants many small per-warp arenas (occupancy), the dense
 # kernel few large ones (long segments; it pipelines its own loads)
 DEFAULT_TILE = {"list": int(os.environ.get("PFZ_TILE_LIST", "512")), "dense": int(os.environ.get("PFZ_TILE_DENSE", "1024")),
-                "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1024")), "block": int(os.environ.get("PFZ_TILE_BLOCK", "1024")),
+                "dense32": int(os.environ.get("PFZ_TILE_DENSE32", "1024")), "block": int(os.environ.get("PFZ_TILE_BLOCK", "2048")),
                 "hash": 65536}
 BLOCK_TILE_STEP, BLOCK_TILE_MAX = 128, 4096
-BLOCK_ROWS = int(os.environ.get("PFZ_BLOCK_ROWS", "8"))           # from-rows (= warps) per CTA of the block kernel: 8 or 16
-BLOCK_ACC_BITS = int(os.environ.get("PFZ_BLOCK_ACC_BITS", "32"))  # 32: one accumulator per word (2^-26); 16: two per word (2^-15)
+BLOCK_ROWS = int(os.environ.get("PFZ_BLOCK_ROWS", "8"))           # from-rows (= warps) per CTA of the block kernel: 4, 8 or 16
+BLOCK_ACC_BITS = int(os.environ.get("PFZ_BLOCK_ACC_BITS", "16"))  # 16: two accumulators per word (unit 2^-15); 32: one per word (2^-26)
 
 
 class SparseIndex:
@@ -435,8 +435,11 @@ class SparseIndex:
         if tile is None:
             tile = DEFAULT_TILE[variant]
         tile = max(64, min(int(tile), ((max(n, 1) + 63) // 64) * 64))
-        if variant == "block":                                # the block kernel scans its accumulators 128 cells per warp step
-            tile = min(BLOCK_TILE_MAX, max(BLOCK_TILE_STEP, (tile + BLOCK_TILE_STEP - 1) // BLOCK_TILE_STEP * BLOCK_TILE_STEP))
+        self.acc_bits = 32
+        if variant == "block":                                # the block kernel scans its accumulators 128 words per warp step
+            self.acc_bits = 16 if BLOCK_ACC_BITS == 16 else 32
+            step = BLOCK_TILE_STEP * (2 if self.acc_bits == 16 else 1)
+            tile = min(BLOCK_TILE_MAX, max(step, (tile + step - 1) // step * step))
         self.tile = tile
         self.n_to = n
         self.n_vocab = csr.n_cols
@@ -459,7 +462,10 @@ class SparseIndex:
         _lib.call("pfz_index_build", _p(csr.indptr), _p(csr.indices), _p(csr.data), n, self.n_vocab, tile,
                   self.n_tiles, flags, _p(self.seg), _p(self.post_idx), _p(self.post_val), _p(self.post_val32), _p(self.term_maxw), _p(ws), _stream())
         if variant in ("block", "hash") and n > 0:
-            _lib.call("pfz_index_pack_q26", _p(self.post_idx), _p(self.post_val), ctypes.c_void_p(self.seg.data_ptr() + 4 * ncell), _p(self.post_pk), _stream())
+            if self.acc_bits == 16:                             # {word offset | half-word selector, w15}: what the 16-bit update consumes
+                _lib.call("pfz_index_pack_q15", _p(self.post_idx), _p(self.post_val), ctypes.c_void_p(self.seg.data_ptr() + 4 * ncell), tile, _p(self.post_pk), _stream())
+            else:
+                _lib.call("pfz_index_pack_q26", _p(self.post_idx), _p(self.post_val), ctypes.c_void_p(self.seg.data_ptr() + 4 * ncell), _p(self.post_pk), _stream())
 
 
 DENSE32_MAX_ROW_NNZ = 128
@@ -521,7 +527,7 @@ def _spcos_block(a, index, k, min_similarity, self_match, from_index_base, to_in
     tv = torch.empty((n_splits, max(n_from, 1), k), dtype=torch.float64, device=dev)
     _lib.call("pfz_spcos_topk_block", _p(a.indptr), _p(a.indices), _p(a.data), n_from, nnz_cap, _p(index.seg), _p(index.post_pk),
               _p(index.csr.indptr), _p(index.csr.indices), _p(index.csr.data), index.n_vocab, index.tile, index.n_tiles, index.n_to, k,
-              float(min_similarity), int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, BLOCK_ROWS, BLOCK_ACC_BITS if index.tile % 256 == 0 else 32, _p(ti), _p(tv), _p(err),
+              float(min_similarity), int(bool(self_match)), int(from_index_base), int(to_index_base), n_splits, BLOCK_ROWS, index.acc_bits, _p(ti), _p(tv), _p(err),
               _p(ws), _stream())
     if n_splits > 1:
         oi = torch.empty((max(n_from, 1), k), dtype=torch.int32, device=dev)

@@ -296,13 +296,14 @@ def test_shard_emulation_equals_unsharded(pf):
     assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
 
 
-@pytest.mark.parametrize("variant", ["dense32", "block", "block16"])
+@pytest.mark.parametrize("variant", ["dense32", "block", "block16", "block32", "block16x4"])
 def test_dense32_many_exact_ties_and_identical_rows(pf, monkeypatch, variant):
     """The fp32 filter must hand every row near the k-th key to the exact re-scoring: lists full of duplicates
     (scores exactly 1.0 and large groups of exactly tied scores)."""
     polyfuzz_b200, engine = pf
-    if variant == "block16":
-        monkeypatch.setattr(engine, "BLOCK_ACC_BITS", 16); variant = "block"
+    if variant.startswith("block") and variant != "block":
+        monkeypatch.setattr(engine, "BLOCK_ACC_BITS", 32 if variant == "block32" else 16)
+        monkeypatch.setattr(engine, "BLOCK_ROWS", 4 if variant.endswith("x4") else 8); variant = "block"
     _force_variant(monkeypatch, engine, variant)
     names = ["acme holdings inc"] * 40 + ["dup dup llc"] * 600 + ["acme holding inc"] * 40 + [f"zeta {i % 5} llc" for i in range(300)] + ["unique name ltd"]
     m = polyfuzz_b200.TFIDF(min_similarity=0.0, top_n=12)
@@ -380,7 +381,7 @@ def test_titles_slice_vectoriser_matches_reference_on_gpu(pf, golden_dir, tag, r
         _csr_eq(v.emit(rows), g[f"{tag}_{name}_indptr"], g[f"{tag}_{name}_indices"], g[f"{tag}_{name}_data"], g[f"{tag}_{name}_shape"])
 
 
-@pytest.mark.parametrize("acc_bits,rows", [(32, 8), (16, 8), (16, 16), (32, 16)])
+@pytest.mark.parametrize("acc_bits,rows", [(32, 8), (16, 8), (16, 16), (32, 16), (16, 4), (32, 4)])
 def test_block_variant_long_rows_split_blocks_and_margin(pf, monkeypatch, acc_bits, rows):
     """The from-row-block kernel at its contract's edge: rows of ~100-128 distinct trigrams (blocks of 8 such rows exceed the
     512-entry block table and are split in halves), mixed with short rows, duplicates and empty rows; tile 128 and a tile
