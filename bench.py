@@ -387,7 +387,7 @@ def sub_c5(args, dev, rank, local_rank, world, comm, barrier, flush, peak):
         dist.all_reduce(tot, op=dist.ReduceOp.MAX); dist.all_reduce(k2, op=dist.ReduceOp.MAX); dist.all_reduce(P, op=dist.ReduceOp.SUM)
     t = float(tot.item()) / len(ms) * 1e-3
     P = float(P.item())
-    s_bytes = 4 if res["index"].variant == "dense32" else 8
+    s_bytes = 4 if res["index"].variant in ("dense32", "block", "hash") else 8     # stored weight: 32-bit fixed point / fp32, else fp64
     b_alg = P * (4 + s_bytes) + nf * 12.0 * world + float(n) * TOP_N * 12 * world
     k2_t = float(k2.item()) * 1e-3
     return {"workload": "TF-IDF char-trigram top-10, %d x %d uniform 8..32-char strings, to_list row-sharded x%d (BASELINE configs[4])" % (n, n, world),

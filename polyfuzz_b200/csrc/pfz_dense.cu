@@ -488,8 +488,8 @@ int pfz_dense_cos_topk(const void *x_bf16, const void *y_bf16, int32_t n_from, i
         PFZ_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
         enc = (EncodeTiledFn)fn;
     }
-    const char *env2 = getenv("PFZ_K4_2CTA");                   // cta_group::2 variant (CTA pairs, half the to-operand traffic per SM)
-    const bool two_cta = env2 ? atoi(env2) != 0 : false;
+    const char *env2 = getenv("PFZ_K4_2CTA");                   // cta_group::2 variant (CTA pairs, half the to-operand traffic per SM): the
+    const bool two_cta = env2 ? atoi(env2) != 0 : true;         // default since it was validated on hardware (13.66 vs 14.04 ms at 100k x 100k x 768); 0 = single-CTA kernel
     CUtensorMap mx, my;
     if (make_map(enc, &mx, x_bf16, n_from, d, DM)) return 1;
     if (make_map(enc, &my, y_bf16, n_to, d, two_cta ? DN / 2 : DN)) return 1;

@@ -11,7 +11,8 @@
 // the CTA walks the row's (term, tile) segments once, and every posting is one hash insert (atom.shared.cas) plus one
 // fire-and-forget fixed-point add (red.shared.add.u32, unit 2^-26, see pfz_spcos_block.cu).  The table then is scanned
 // once: sums above the row's threshold are re-scored exactly from the two CSR rows and inserted into the top-k list.
-// A row whose postings exceed half the table is processed in several passes over disjoint tile ranges.
+// A row whose postings exceed half the table is processed in several passes over disjoint tile ranges; a pass whose table
+// still fills is redone over halved to-row ranges, so the table size is a performance knob only.
 #include <stdlib.h>
 #include "pfz_common.cuh"
 
@@ -158,6 +159,13 @@ __global__ void __launch_bounds__(HASH_NT) spcos_hash_kernel(const HashParams P)
             if (ta >= tb) break;
             const int ntp = tb - ta;
             const int npairs = mm * ntp;
+            // The pass covers the to-rows [r_lo, r_lo + r_w) of each of its tiles -- normally the whole tile.  When the table
+            // fills (a row that visits far more postings in these tiles than the estimate), the table is cleared and the range
+            // halved, so no input can overflow it.
+            int r_lo = 0, r_w = T;
+            while (r_lo < T) {
+            const unsigned f_lo = (unsigned)r_lo, f_hi = (unsigned)min(T, r_lo + r_w);
+            if (tid == 0) sh[4] = 0;
             // ---- accumulate: (term, tile) segments -> work items -> hash inserts ------------------------------------
             for (int pb = 0; pb < npairs; pb += HASH_NT) {
                 const int p = pb + tid;
@@ -191,20 +199,29 @@ __global__ void __launch_bounds__(HASH_NT) spcos_hash_kernel(const HashParams P)
                         const HItem it = items[q];
                         if (lane < it.cnt) {
                             const uint2 pk = __ldg(P.post_pk + it.off + lane);
-                            const unsigned key = it.keybase + pk.x;                 // to-row local to the shard
-                            const unsigned add = __umulhi(it.v, pk.y) + 1u;
-                            unsigned h = (key * 2654435761u) >> (32 - LOGH);
-                            bool done = false;
-                            for (int probe = 0; probe < H; ++probe) {
-                                const unsigned old = atomicCAS(&keys[h], HASH_EMPTY, key);
-                                if (old == HASH_EMPTY || old == key) { atomicAdd(&vals[h], add); done = true; break; }
-                                h = (h + 1) & (H - 1);
+                            if (pk.x >= f_lo && pk.x < f_hi) {
+                                const unsigned key = it.keybase + pk.x;             // to-row local to the shard
+                                const unsigned add = __umulhi(it.v, pk.y) + 1u;
+                                unsigned h = (key * 2654435761u) >> (32 - LOGH);
+                                bool done = false;
+                                for (int probe = 0; probe < (H < 512 ? H : 512); ++probe) {
+                                    const unsigned old = atomicCAS(&keys[h], HASH_EMPTY, key);
+                                    if (old == HASH_EMPTY || old == key) { atomicAdd(&vals[h], add); done = true; break; }
+                                    h = (h + 1) & (H - 1);
+                                }
+                                if (!done) sh[4] = 1;                               // table (nearly) full: this range is redone in halves
                             }
-                            if (!done) atomicExch(P.err_flag, 2);                    // table full: the caller retries with more passes / a bigger table
                         }
                     }
                     __syncthreads();
                 }
+            }
+            if (sh[4] != 0 && r_w > 1) {                   // (uniform: written before the barrier that ends the accumulate phase)
+                __syncthreads();
+                for (int q = tid; q < H; q += HASH_NT) { keys[q] = HASH_EMPTY; vals[q] = 0u; }
+                r_w = (r_w + 1) >> 1;
+                __syncthreads();
+                continue;
             }
             // ---- select: scan the table, exact re-scoring of the sums above the threshold --------------------------------
             unsigned gate = sh_thr[0];
@@ -287,6 +304,8 @@ __global__ void __launch_bounds__(HASH_NT) spcos_hash_kernel(const HashParams P)
                 __syncthreads();
                 if (!more) break;
                 gate = max(gate, sh_thr[0]);
+            }
+            r_lo += r_w;
             }
         }
         if (w == 0 && lane < K) {

@@ -428,3 +428,24 @@ def test_hash_variant_uniform_strings_vs_oracle(pf, monkeypatch, slots, k, ms, s
     oi, ov = onative.spdot_topn(csr_from.to_scipy(), csr_to.to_scipy(), k, ms, self_match=self_match, n_threads=16)
     np.testing.assert_array_equal(idx.cpu().numpy(), oi)
     np.testing.assert_array_equal(val.cpu().numpy(), ov)
+
+
+def test_hash_variant_dense_rows_never_overflow_the_table(pf, monkeypatch):
+    """The hash kernel on input far denser than its cost model assumes (company names: a from-row visits ~20 000 postings per
+    65 536-row tile against a 2 048-slot table): passes whose table fills are redone over halved to-row ranges, results stay
+    bit-identical to the oracle and no error flag is raised."""
+    polyfuzz_b200, engine = pf
+    from polyfuzz_b200 import synth
+    monkeypatch.setattr(engine, "HASH_SLOTS", 2048)
+    to = synth.company_names(70_000, seed=3)
+    frm = synth.company_names(200, seed=4) + [to[5], to[69_999], ""]
+    v = engine.NgramTfidf((3, 3), True, True)
+    rows_to, rows_from = v.fit_rows([to, frm])
+    csr_to, csr_from = v.emit(rows_to), v.emit(rows_from)
+    ix = engine.SparseIndex(csr_to, variant="hash")
+    assert ix.n_tiles == 2
+    idx, val = engine.spcos_topk(csr_from, ix, 10, 0.0)
+    assert int(ix._hash_err.item()) == 0
+    oi, ov = onative.spdot_topn(csr_from.to_scipy(), csr_to.to_scipy(), 10, 0.0, self_match=False, n_threads=16)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(val.cpu().numpy(), ov)
