@@ -63,7 +63,8 @@ def build(force=False, verbose=False):
     build_hostpack(force)
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + sources()
+    extra = os.environ.get("PFZ_NVCC_EXTRA", "").split()          # developer builds (e.g. -DPFZ_B3_TIMING)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-o", LIB] + sources()
     env = dict(os.environ)
     # the image's CC wrapper lacks OpenMP specs; nvcc only needs a plain host g++
     env.pop("CC", None); env.pop("CXX", None)

@@ -1,5 +1,5 @@
 // pfz_spcos_block.cu -- K2, from-row-BLOCK variant (PFZ_K2_BLOCK): sparse cosine + fused per-row top-k where a CTA of
-// BF warps scores a block of BF from-rows (8 or 16) against a to-tile at a time, so that ONE load of a posting chunk
+// BF warps scores a block of BF from-rows (4, 8 or 16) against a to-tile at a time, so that ONE load of a posting chunk
 // serves every from-row of the block that contains the term.
 //
 // Replaces sparse_dot_topn.awesome_cossim_topn (call site polyfuzz/models/_utils.py:82) and the reference's Python
@@ -13,32 +13,31 @@
 //   * from-rows are CLUSTERED by their three heaviest terms (sort of a 64-bit key), so a block of consecutive rows
 //     shares most heavy terms (company names: one posting load serves ~4 of 8 rows on average);
 //   * a block table (per block: distinct terms, per term the list of (row-in-block, weight)) is built once per call;
-//   * accumulators acc[BF][tile] are 32-bit FIXED-POINT sums (unit 2^-26) in shared memory, updated with
-//     red.shared.add.u32: a fire-and-forget integer atomic that retires at one warp-update per SM-cycle on B200
+//   * accumulators acc[BF][tile] are FIXED-POINT sums in shared memory, updated with red.shared.add.u32: a
+//     fire-and-forget integer atomic that retires at one warp-update per SM-cycle on B200
 //     (profiles/atoms_probe_r02.txt; a ld/fma/st read-modify-write chain managed 4.3 cycles with 8 warps and 33 with
-//     one).  Integer adds are associative, so the warps of the CTA share one accumulator tile and consume the
-//     unit's work items (<= 32 postings of one term each) in any order, with no hazards and no ordering;
+//     one; float and 64-bit shared-memory adds are CAS loops).  Integer adds are associative, so the warps of the CTA share
+//     one accumulator tile and consume the unit's work items (<= 32 postings of one term each) in any order, with no
+//     hazards and no ordering.  Default: two 16-bit accumulators per word (unit 2^-15, to-rows j and j + tile/2 share
+//     word j) -- twice the tile in the same shared memory; 32-bit accumulators (unit 2^-26) remain selectable;
 //   * the sums only FILTER (as in PFZ_K2_DENSE32): after the unit's updates each warp scans (and clears) the
-//     accumulators of ITS from-row against the row's threshold (k-th key - MARGIN, or a lane-maxima bound while the
-//     list is still filling); cells above it are re-scored exactly -- fp64, ascending terms, products rounded before
-//     the add -- by merging the two CSR rows, and inserted into the row's top-k list (registers of that warp).
-// Fixed point: from-weight v_i = floor(v * 2^32), posting weight w_i = round(w * 2^26), update = mulhi(v_i, w_i):
-// + 1 (so that every common term registers): -0.51 < update - v*w*2^26 <= 1.5 units, so a row of <= 128 terms is within
-// 192 units = 2.9e-6 of the exact score.
+//     accumulators of ITS from-row against the row's gate (the K-th largest sum seen so far - margin, or a
+//     lane-maxima bound while fewer than K sums have been seen); cells above it are queued and, at the end of the block,
+//     re-scored exactly -- fp64, ascending terms, products rounded before the add -- by merging the two CSR rows.
+// Fixed point, 16-bit: v16 = max(1, floor(v * 2^16)), w15 = max(1, round(w * 2^15)), update = ceil(v16 * w15 / 2^16):
+// -1.01 < update - v*w*2^15 < 2.01 units and >= 1 for every common term; margin 4 m + 2 units for a from-row of m <= 128
+// terms (every half-word stays below 2^15 + 258 < 2^16: no carry into its neighbour).  32-bit: v_i = floor(v * 2^32),
+// w_i = round(w * 2^26), update = mulhi(v_i, w_i) + 1: -0.51 < update - v*w*2^26 <= 1.5 units, margin 1e-5.
 #include <stdlib.h>
 #include "pfz_common.cuh"
 
 namespace pfz {
 
 constexpr double K2B_SCALE = 67108864.0;         // 2^26: fixed-point unit of the accumulators
-constexpr double K2B_MARGIN = 1e-5;              // filter margin: >= 2 x 194 units (two approximate sums are compared by the lane-maxima gate)
-constexpr unsigned K2B_MARGIN_Q = 672u;          // ceil(K2B_MARGIN * 2^26)
-constexpr int ITEM_CAP = 256;                    // work items per batch
-constexpr int BLK_QCAP = 256;                    // candidates a from-row may queue before they are re-scored exactly
+constexpr unsigned K2B_MARGIN_Q = 672u;          // 32-bit mode filter margin 1e-5 in units of 2^-26: >= 2 x 194 units (two approximate sums are compared)
 constexpr int RANK_CAP = 16383;                  // term ranks are capped to 14 bits in the clustering key
 
 struct __align__(16) BlockDesc { int pos0; int nrows; int base; int nterms; };
-struct __align__(16) BItem { int off; int cnt; unsigned fvs; int nf; };
 
 // ---- preparation kernels -------------------------------------------------------------------------------------
 // terms sorted by document frequency in the to-shard, heaviest first: key = (~df) << 32 | term
@@ -210,15 +209,6 @@ __device__ __forceinline__ void red_add_u32(unsigned a, unsigned v) {
     // of the kernel is separated from the updates by __syncthreads()
     asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(v));
 }
-// one posting chunk applied to the N from-rows that hold the term: the N table entries first, the N updates after
-template <int N, bool P16>
-__device__ __forceinline__ void red_group(unsigned cell, const uint2 *fv, unsigned wq, unsigned one, unsigned hi) {
-    uint2 e[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) e[q] = fv[q];
-#pragma unroll
-    for (int q = 0; q < N; ++q) red_add_u32(cell + e[q].x, P16 ? ((__umulhi(e[q].y, wq) + one) << hi) : (__umulhi(e[q].y, wq) + one));
-}
 __device__ __forceinline__ bool blk_key_before(double sa, int ia, double sb, int ib) { return (sa > sb) || (sa == sb && ia < ib); }
 // canonical score of (from-row a, to-row b): common terms in ascending order, product rounded, then added.  The to-row is
 // staged 32 entries at a time with INDEPENDENT loads (one memory latency per chunk instead of one per merge step -- the merge
@@ -241,11 +231,6 @@ __device__ __noinline__ double blk_exact_dot(const int32_t *__restrict__ ai, con
     }
     return s;
 }
-// largest fixed-point value (unit 2^-26) not above x - MARGIN (>= 0): sums above it may reach x
-__device__ __forceinline__ unsigned blk_thr_q(double x) {
-    const double y = (x - K2B_MARGIN) * K2B_SCALE;
-    return y <= 0.0 ? 0u : (unsigned)__double2ll_rd(y);
-}
 // descending bitonic sort of one value per lane: lane r ends up with the r-th largest
 __device__ __forceinline__ unsigned warp_sort_desc_u32(unsigned x, int lane) {
 #pragma unroll
@@ -260,283 +245,10 @@ __device__ __forceinline__ unsigned warp_sort_desc_u32(unsigned x, int lane) {
     return x;
 }
 
-// per-CTA shared-memory arena (bytes), T = tile
-template <int BF, bool P16>
-__host__ __device__ inline size_t blk_arena_bytes(int T) {
-    return (size_t)BF * T * (P16 ? 2 : 4)      // acc
-           + (size_t)(ITEM_CAP + BF) * 16      // items (+ one padding item per warp)
-           + (size_t)BF * 64 * 8               // terms + fvdesc (uint2)
-           + (size_t)BF * 64 * 8               // fv
-           + (size_t)BF * BLK_QCAP * 4         // candidate queue of every warp (= from-row)
-           + 256;                              // scan scratch, descriptor broadcast
-}
-
-// P16: two 16-bit fixed-point accumulators (unit 2^-15) per 32-bit word -- to-rows j and j + tile/2 share a word, so the bank
-// of an update is still (row mod 32) -- which doubles the tile a CTA can hold (half the (block, tile) units, longer posting
-// segments) at a coarser filter: per product -0.52 < update - v*w*2^15 <= 1.51 units, margin 3*m + 2 units for a from-row
-// of m terms (m <= 128: every 16-bit half stays below 2^15 + 194 < 2^16, no carry into its neighbour).
-template <int BF, bool P16>
-__global__ void __launch_bounds__(BF * 32, BF == 8 ? 4 : 2) spcos_block_kernel(const BlockParams P) {
-    constexpr int W = BF, NT = BF * 32, FV_CAP = BF * 64;
-    extern __shared__ __align__(16) unsigned char dyn[];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    const int T = P.tile, K = P.k;
-    unsigned char *base = dyn;
-    const int TW = P16 ? (T >> 1) : T;                                 // 32-bit accumulator words per from-row
-    unsigned *acc = reinterpret_cast<unsigned *>(base);                 base += (size_t)BF * TW * 4;
-    BItem *items = reinterpret_cast<BItem *>(base);                     base += (size_t)(ITEM_CAP + BF) * 16;
-    uint2 *termtab = reinterpret_cast<uint2 *>(base);                   base += (size_t)FV_CAP * 8;      // {term, fvdesc}
-    uint2 *fvtab = reinterpret_cast<uint2 *>(base);                     base += (size_t)FV_CAP * 8;
-    int *cand = reinterpret_cast<int *>(base) + w * BLK_QCAP;           base += (size_t)BF * BLK_QCAP * 4;
-    int *wsum = reinterpret_cast<int *>(base);                          // [W] warp totals of the item scan
-    int *bcast = wsum + 32;                                             // descriptor index broadcast
-
-    for (int q = tid; q < BF * TW; q += NT) acc[q] = 0u;
-    const unsigned acc_s = sm_u32(acc);
-    const uint2 *pk_lane = P.post_pk + lane;
-    const int32_t *__restrict__ seg = P.seg;
-    const int n_tiles = P.n_tiles;
-
-    const int split = blockIdx.y;
-    const int tiles_per = (P.n_tiles + P.n_splits - 1) / P.n_splits;
-    const int tau_lo = split * tiles_per;
-    const int tau_hi = min(P.n_tiles, tau_lo + tiles_per);
-    int32_t *counter = P.counter + split;
-    const double scale = P16 ? 32768.0 : K2B_SCALE;
-    __syncthreads();
-
-    for (;;) {
-        if (tid == 0) bcast[0] = atomicAdd(counter, 1);
-        __syncthreads();
-        const int di = bcast[0];
-        __syncthreads();
-        if (di >= P.n_desc) break;
-        const BlockDesc D = P.descs[di];
-        const int nrows = D.nrows, nterms = D.nterms;
-        if (nrows == 0) continue;
-        // warp w owns from-row w of the block: its CSR slice, threshold, candidate queue and top-k list (lane r = rank r)
-        const bool has_row = w < nrows;
-        int row = 0, a0 = 0, m = 0, stau = -1, sjl = 0;
-        if (has_row) {
-            row = P.perm[D.pos0 + w];
-            a0 = P.a_indptr[row]; m = P.a_indptr[row + 1] - a0;
-            const int64_t self_j = P.from_base + row - P.to_base;       // local to-row of the diagonal
-            if (P.self_match && self_j >= 0 && self_j < (int64_t)P.n_to) { stau = (int)(self_j / T); sjl = (int)(self_j - (int64_t)stau * T); }
-        }
-        double tv = P.min_sim; int ti = -1;
-        double kv = P.min_sim; int ki = -1;
-        // filter margin in accumulator units, and the largest value not above (x - margin)
-        const unsigned MQ = P16 ? (unsigned)(3 * m + 2) : K2B_MARGIN_Q;
-        auto thr_of = [&](double x) { const double y = x * scale - (double)MQ; return y <= 0.0 ? 0u : (unsigned)__double2ll_rd(y); };
-        unsigned thr = thr_of(fmax(P.min_sim, 0.0));
-        // the K largest fixed-point sums seen so far (lane r = r-th largest): they, not the exact list, drive the filter
-        // threshold, so that the exact re-scoring can wait until the block is done (a to-row of the final top-k has an exact
-        // score >= the K-th best exact score seen >= a_K - err, hence a sum >= a_K - 2 err > a_K - MARGIN)
-        unsigned av = 0u, akth = 0u;
-        int ncand = 0;
-        int nfv_total = has_row && lane == 0 ? m : 0;
-        for (int u = tid; u < nterms; u += NT) termtab[u] = make_uint2((unsigned)P.blk_terms[D.base + u], (unsigned)P.blk_fvdesc[D.base + u]);
-        // (row, weight) entries: the table holds exactly the sum of the rows' nnz
-        if (lane == 0) wsum[w] = nfv_total;
-        __syncthreads();
-        nfv_total = 0;
-#pragma unroll
-        for (int q = 0; q < W; ++q) nfv_total += wsum[q];
-        for (int e = tid; e < nfv_total; e += NT) fvtab[e] = P.blk_fv[D.base + e];
-        __syncthreads();
-
-        // exact scoring + insertion of up to 32 queued candidates of this warp's row (one per lane)
-        auto score_round = [&](int off, int n_round) {
-            double sc = 0.0; int j = -1; bool cnd = false;
-            if (lane < n_round) {
-                const int jloc = cand[off + lane];
-                const int b0 = P.b_indptr[jloc];
-                sc = blk_exact_dot(P.a_indices + a0, P.a_data + a0, m, P.b_indices + b0, P.b_data + b0, P.b_indptr[jloc + 1] - b0);
-                j = (int)(P.to_base + jloc);
-                cnd = blk_key_before(sc, j, kv, ki);
-                if (stau >= 0 && jloc == stau * T + sjl) cnd = false;
-            }
-            unsigned cm = __ballot_sync(FULL, cnd);
-            while (cm) {
-                const int src = __ffs(cm) - 1;
-                const double cs = shfl_d(sc, src);
-                const int cj = __shfl_sync(FULL, j, src);
-                const bool stays = (lane < K) && blk_key_before(tv, ti, cs, cj);
-                const int pos = __popc(__ballot_sync(FULL, stays));
-                const double uv = __shfl_up_sync(FULL, tv, 1);
-                const int ui = __shfl_up_sync(FULL, ti, 1);
-                if (lane > pos) { tv = uv; ti = ui; }
-                else if (lane == pos) { tv = cs; ti = cj; }
-                kv = shfl_d(tv, K - 1);
-                ki = __shfl_sync(FULL, ti, K - 1);
-                cnd = cnd && lane != src && blk_key_before(sc, j, kv, ki);
-                cm = __ballot_sync(FULL, cnd);
-            }
-            if (ki >= 0) thr = thr_of(kv);
-        };
-        auto drain = [&]() {                                // exact re-scoring of the queue, 32 candidates per round, newest first
-            while (ncand > 0) {
-                const int n_round = min(32, ncand);
-                __syncwarp();
-                score_round(ncand - n_round, n_round);
-                ncand -= n_round;
-            }
-            __syncwarp();
-        };
-
-        for (int tau = tau_lo; tau < tau_hi; ++tau) {
-            bool any_post = false;
-            for (int tb = 0; tb < nterms; tb += NT) {
-                const int u = tb + tid;
-                int s = 0, len = 0, nch = 0, incl = 0; unsigned fvd = 0u;
-                if (tb + (w << 5) < nterms) {                     // (warp-uniform: a block has ~50 terms, warps 2..7 usually skip this)
-                    if (u < nterms) {
-                        const uint2 tt = termtab[u];
-                        fvd = tt.y;
-                        const int64_t c = (int64_t)tt.x * n_tiles + tau;
-                        s = seg[c];
-                        len = seg[c + 1] - s;
-                    }
-                    nch = (len + 31) >> 5;
-                    incl = warp_incl_scan(nch);
-                }
-                if (lane == 31) wsum[w] = incl;
-                __syncthreads();
-                int woff, total;
-                {
-                    const int x = lane < W ? wsum[lane] : 0;       // per-warp item counts -> this warp's offset and the unit's total
-                    const int xs = warp_incl_scan(x);
-                    woff = __shfl_sync(FULL, xs - x, w);
-                    total = __shfl_sync(FULL, xs, W - 1);
-                }
-                if (total == 0) { __syncthreads(); continue; }
-                any_post = true;
-                const int first = woff + incl - nch;                  // id of this thread's first work item
-                const unsigned fvs = fvd >> 5;                      // index of the term's first (row, weight) entry
-                const int nf = (int)(fvd & 31u);
-                for (int start = 0; start < total; start += ITEM_CAP) {
-                    for (int c = 0; c < nch; ++c) {
-                        const int id = first + c - start;
-                        if (id >= 0 && id < ITEM_CAP) { BItem it; it.off = s + 32 * c; it.cnt = len - 32 * c; it.fvs = fvs; it.nf = nf; items[id] = it; }
-                    }
-                    if (tid < W) { BItem it; it.off = 0; it.cnt = 0; it.fvs = 0u; it.nf = 0; items[min(ITEM_CAP, total - start) + tid] = it; }
-                    __syncthreads();
-                    const int nb = min(ITEM_CAP, total - start);
-                    // each warp walks its items (w, w + W, ...) with the NEXT item's posting chunk already in flight; W padding
-                    // items (cnt = 0, nf = 0) behind the last one keep the loop free of bounds checks
-                    BItem it = items[w]; uint2 pk = make_uint2(0u, 0u);
-                    if (lane < it.cnt) pk = __ldg(pk_lane + it.off);
-                    for (int i = w; i < nb; i += W) {
-                        const BItem nit = items[i + W]; uint2 npk = make_uint2(0u, 0u);
-                        if (lane < nit.cnt) npk = __ldg(pk_lane + nit.off);
-                        // idle lanes of a partial chunk add 0 to cell `lane` of each row (distinct banks; no predicates in the loop);
-                        // active lanes add mulhi(v_i, w_i) + 1, so that every common term registers (sum > 0)
-                        const bool on = lane < it.cnt;
-                        const unsigned jl = on ? pk.x : (unsigned)lane, one = on ? 1u : 0u;
-                        const unsigned wq = on ? (P16 ? ((pk.y + 1024u) >> 11) : pk.y) : 0u;       // 2^-15 units when packed
-                        const unsigned hi = P16 && jl >= (unsigned)TW ? 16u : 0u;                  // upper half-word: to-rows tile/2 ..
-                        const unsigned cell = acc_s + ((P16 ? (hi ? jl - (unsigned)TW : jl) : jl) << 2);
-                        const uint2 *fv = reinterpret_cast<const uint2 *>(fvtab) + it.fvs;
-                        int nf = it.nf;
-                        if (BF > 8) { while (nf > 8) { red_group<8, P16>(cell, fv, wq, one, hi); fv += 8; nf -= 8; } }
-                        switch (nf) {                             // straight-line code per row count: table entries first, updates after
-                            case 1: red_group<1, P16>(cell, fv, wq, one, hi); break;
-                            case 2: red_group<2, P16>(cell, fv, wq, one, hi); break;
-                            case 3: red_group<3, P16>(cell, fv, wq, one, hi); break;
-                            case 4: red_group<4, P16>(cell, fv, wq, one, hi); break;
-                            case 5: red_group<5, P16>(cell, fv, wq, one, hi); break;
-                            case 6: red_group<6, P16>(cell, fv, wq, one, hi); break;
-                            case 7: red_group<7, P16>(cell, fv, wq, one, hi); break;
-                            case 8: red_group<8, P16>(cell, fv, wq, one, hi); break;
-                            default: break;
-                        }
-                        it = nit; pk = npk;
-                    }
-                    __syncthreads();
-                }
-            }
-            if (!__syncthreads_or(any_post)) continue;
-            // scan + clear: warp w scans the accumulators of its row against the row's threshold
-            if (has_row) {
-                uint4 *rowp = reinterpret_cast<uint4 *>(acc + (size_t)w * TW);
-                if (stau == tau) {                                     // the diagonal never competes
-                    if (lane == 0) {
-                        if (P16) acc[(size_t)w * TW + (sjl >= TW ? sjl - TW : sjl)] &= (sjl >= TW ? 0x0000ffffu : 0xffff0000u);
-                        else acc[(size_t)w * TW + sjl] = 0u;
-                    }
-                    __syncwarp();
-                }
-                // largest accumulator of a word group: plain maximum, or the maximum over the 16-bit halves
-                auto wmax = [&](const uint4 &v) -> unsigned {
-                    if (!P16) return max(max(v.x, v.y), max(v.z, v.w));
-                    const unsigned m2 = __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w));
-                    return max(m2 & 0xffffu, m2 >> 16);
-                };
-                unsigned gate = max(thr, akth > MQ ? akth - MQ : 0u);
-                if (akth == 0u) {
-                    // fewer than K sums seen: the K-th largest of the 32 lane maxima bounds the unit's K-th best sum from below
-                    unsigned mx = 0u;
-                    for (int c = lane; c < (TW >> 2); c += 32) mx = max(mx, wmax(rowp[c]));
-                    const unsigned srt = warp_sort_desc_u32(mx, lane);
-                    const unsigned kth = __shfl_sync(FULL, srt, K - 1);
-                    if (kth > MQ) gate = max(gate, kth - MQ);
-                }
-                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                // candidates of one 16-byte group (4 words): queue them and keep the K largest sums for the threshold
-                auto extract = [&](const uint4 &v, int c) {
-#pragma unroll
-                    for (int comp = 0; comp < (P16 ? 8 : 4); ++comp) {
-                        const unsigned word = (comp & 3) == 0 ? v.x : (comp & 3) == 1 ? v.y : (comp & 3) == 2 ? v.z : v.w;
-                        const unsigned x = P16 ? (comp < 4 ? (word & 0xffffu) : (word >> 16)) : word;
-                        const bool take = x > gate;
-                        unsigned tm = __ballot_sync(FULL, take);
-                        if (tm == 0u) continue;
-                        if (ncand + 32 > BLK_QCAP) drain();                 // (rare: > 224 contenders of one row inside one block)
-                        if (take) cand[ncand + __popc(tm & lt)] = tau * T + c * 4 + (comp & 3) + (comp >= 4 ? TW : 0);
-                        ncand += __popc(tm);
-                        while (tm) {
-                            const int src = __ffs(tm) - 1; tm &= tm - 1;
-                            const unsigned cx = __shfl_sync(FULL, x, src);
-                            if (cx <= akth) continue;
-                            const int pos = __popc(__ballot_sync(FULL, (lane < K) && av >= cx));
-                            const unsigned up = __shfl_up_sync(FULL, av, 1);
-                            if (lane > pos) av = up; else if (lane == pos) av = cx;
-                            akth = __shfl_sync(FULL, av, K - 1);
-                        }
-                        if (akth > MQ) gate = max(gate, akth - MQ);
-                        __syncwarp();
-                    }
-                };
-                const int ng = TW >> 2;                                // 16-byte groups of the row
-                for (int c0 = 0; c0 < ng; c0 += 64) {                   // two groups per lane and vote
-                    const int c = c0 + lane, c2 = c + 32;
-                    const uint4 v0 = rowp[c]; rowp[c] = z;
-                    uint4 v1 = z;
-                    if (c2 < ng) { v1 = rowp[c2]; rowp[c2] = z; }
-                    if (!__any_sync(FULL, max(wmax(v0), wmax(v1)) > gate)) continue;
-                    if (__any_sync(FULL, wmax(v0) > gate)) extract(v0, c);
-                    if (__any_sync(FULL, wmax(v1) > gate)) extract(v1, c2);
-                }
-            }
-            __syncthreads();
-        }
-        if (has_row) {
-            drain();                                            // all warps of the CTA re-score their rows' contenders concurrently
-            if (lane < K) {
-                const size_t o = ((size_t)split * P.n_from + row) * K + lane;
-                P.top_idx[o] = ti;
-                P.top_val[o] = (ti >= 0) ? tv : 0.0;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ---- main kernel, version 3 ------------------------------------------------------------------------------------
-// Same algorithm as spcos_block_kernel (fixed-point red.shared accumulators shared by the CTA, filter + exact re-scoring), laid
-// out for instruction count and registers after the ncu profile of version 2 (profiles/k2_r02_block_v2_metrics.txt: 67 warp
-// instructions per work item, 43 per 256 scanned cells, local-memory spills in both loops, 5 barriers per (block, tile) unit):
+// ---- main kernel (version 3) -----------------------------------------------------------------------------------
+// Laid out for instruction count and registers after the ncu profile of version 2 (one monolithic kernel;
+// profiles/k2_r02_block_v2_metrics.txt: 67 warp instructions per work item, 43 per 256 scanned cells, local-memory spills in
+// both loops, 5 barriers per (block, tile) unit):
 //   * everything rare -- queueing candidates, maintaining the K largest sums, exact re-scoring, the top-k list -- lives in
 //     NOINLINE functions whose state is in shared memory (B3Row), so the two hot loops (work items, scan) keep a handful of
 //     registers and nothing spills;
@@ -549,7 +261,13 @@ __global__ void __launch_bounds__(BF * 32, BF == 8 ? 4 : 2) spcos_block_kernel(c
 //   * 16-bit mode: update = ceil(v16 * w15 / 2^16) placed in its half-word by one byte permute (IMAD + PRMT), v16 =
 //     max(1, floor(v * 2^16)), w15 = max(1, round(w * 2^15)) pre-packed with the word offset and the permute selector
 //     (pfz_index_pack_q15): -1.01 < update - v*w*2^15 < 2.01 units per product, >= 1 for every common term; margin 4 m + 2.
-constexpr int B3_ICAP_PER_ROW = 64;              // staged work items per unit = 64 x block rows; larger units walk the term table directly
+#ifndef PFZ_B3_ICAP_PER_ROW
+#define PFZ_B3_ICAP_PER_ROW 64
+#endif
+#ifndef PFZ_B3_MIN_CTAS
+#define PFZ_B3_MIN_CTAS(BF) (32 / (BF))
+#endif
+constexpr int B3_ICAP_PER_ROW = PFZ_B3_ICAP_PER_ROW;              // staged work items per unit = 64 x block rows; larger units walk the term table directly
 constexpr int B3_QCAP = 128;                     // candidates a from-row may queue before they are re-scored exactly
 constexpr int B3_DEPTH = 3;                      // posting chunks in flight per warp
 
@@ -828,8 +546,18 @@ __host__ __device__ inline size_t blk3_arena_bytes(int T) {
            + sizeof(B3Ctx) + 64;               // context, counters
 }
 
+#ifdef PFZ_B3_TIMING
+// developer instrumentation (build with PFZ_NVCC_EXTRA=-DPFZ_B3_TIMING, read with tools/b3_timing.py): SM cycles per phase,
+// summed over the warps -- table, wait A, items, wait B, scan, exact re-scoring, wait at the end of the block
+__device__ unsigned long long g_b3_cycles[8];
+#define B3_TICK(slot)                                                                                \
+    do { const long long _now = clock64(); if (lane == 0) atomicAdd(&g_b3_cycles[slot], (unsigned long long)(_now - _t)); _t = clock64(); } while (0)
+#else
+#define B3_TICK(slot) do { } while (0)
+#endif
+
 template <int BF, bool P16>
-__global__ void __launch_bounds__(BF * 32, 32 / BF) spcos_blk3_kernel(const BlockParams P) {
+__global__ void __launch_bounds__(BF * 32, PFZ_B3_MIN_CTAS(BF)) spcos_blk3_kernel(const BlockParams P) {
     constexpr int W = BF, NT = BF * 32, FV_CAP = BF * 64, B3_ICAP = BF * B3_ICAP_PER_ROW;
     extern __shared__ __align__(16) unsigned char dyn[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -924,8 +652,12 @@ __global__ void __launch_bounds__(BF * 32, 32 / BF) spcos_blk3_kernel(const Bloc
         }
         // (the first barrier A below publishes fvtab and the row states)
 
+#ifdef PFZ_B3_TIMING
+        long long _t = clock64();
+#endif
         for (int tau = tau_lo; tau < tau_hi; ++tau) {
             const int par = tau & 1;
+            B3_TICK(4);                                                   // (scan of the previous tile / block prologue)
             // ---- table phase: one work item per 32 postings of a (term, tile) segment ----
             auto emit = [&](int s, int len, unsigned fva, int nf) {
                 const int nch = (len + 31) >> 5;
@@ -960,7 +692,9 @@ __global__ void __launch_bounds__(BF * 32, 32 / BF) spcos_blk3_kernel(const Bloc
                     emit(s, len, fva, nf);
                 }
             }
+            B3_TICK(0);                                                   // table
             __syncthreads();                                              // ---- barrier A: items visible; every row of the previous tile scanned
+            B3_TICK(1);                                                   // wait at A
             const int total = icnt[par];
             if (tid == 0) icnt[par ^ 1] = 0;
             if (total == 0) { __syncthreads(); continue; }                 // (uniform; the barrier orders the counter reset)
@@ -980,7 +714,9 @@ __global__ void __launch_bounds__(BF * 32, 32 / BF) spcos_blk3_kernel(const Bloc
                     }
                 }
             }
+            B3_TICK(2);                                                   // items
             __syncthreads();                                              // ---- barrier B: every update of the unit done
+            B3_TICK(3);                                                   // wait at B
             // ---- scan + clear: warp w scans the accumulators of its row against the row's threshold ----
             if (has_row) {
                 if (stau == tau) {                                     // the diagonal never competes
@@ -999,6 +735,7 @@ __global__ void __launch_bounds__(BF * 32, 32 / BF) spcos_blk3_kernel(const Bloc
                 }
             }
         }
+        B3_TICK(4);
         if (has_row) {
             __syncwarp();
             blk3_drain(cx, rs);
@@ -1009,13 +746,16 @@ __global__ void __launch_bounds__(BF * 32, 32 / BF) spcos_blk3_kernel(const Bloc
                 P.top_val[o] = (ti >= 0) ? rs->tv[lane] : 0.0;
             }
         }
+        B3_TICK(5);                                                       // exact re-scoring at the end of the block
         __syncthreads();
+        B3_TICK(6);                                                       // wait at the end of the block
     }
 }
 
 template <int BF, bool P16>
 static int launch_blk3(const BlockParams &P, int n_groups, int sms, int smem_max, cudaStream_t st) {
-    const size_t arena = (blk3_arena_bytes<BF, P16>(P.tile) + 15) & ~(size_t)15;
+    size_t arena = (blk3_arena_bytes<BF, P16>(P.tile) + 15) & ~(size_t)15;
+    { const char *e = getenv("PFZ_BLOCK_PAD_SMEM"); if (e) arena += (size_t)atoi(e); }      // developer knob: occupancy experiments
     PFZ_REQUIRE(arena <= (size_t)smem_max, "pfz_spcos_topk_block: tile %d x %d rows needs %zu B shared memory > %d available", P.tile, BF, arena, smem_max);
     PFZ_CUDA_OK(cudaFuncSetAttribute(spcos_blk3_kernel<BF, P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)arena));
     int occ = 0;
@@ -1058,22 +798,6 @@ static BlockWs block_ws_layout(int64_t n_from, int64_t nnz_cap, int64_t n_vocab,
     L.counters = o; o += align256((size_t)(n_splits + 1) * 4);
     L.total = o;
     return L;
-}
-
-template <int BF, bool P16>
-static int launch_block(const BlockParams &P, int n_groups, int sms, int smem_max, cudaStream_t st) {
-    const size_t arena = (blk_arena_bytes<BF, P16>(P.tile) + 15) & ~(size_t)15;
-    PFZ_REQUIRE(arena <= (size_t)smem_max, "pfz_spcos_topk_block: tile %d x %d rows needs %zu B shared memory > %d available", P.tile, BF, arena, smem_max);
-    PFZ_CUDA_OK(cudaFuncSetAttribute(spcos_block_kernel<BF, P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)arena));
-    int occ = 0;
-    PFZ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spcos_block_kernel<BF, P16>, BF * 32, arena));
-    if (occ < 1) occ = 1;
-    int gx = sms * occ;
-    if (gx > 2 * n_groups) gx = 2 * n_groups;
-    if (P.n_splits > 1) { gx = (gx + P.n_splits - 1) / P.n_splits; if (gx < 1) gx = 1; }
-    spcos_block_kernel<BF, P16><<<dim3(gx, P.n_splits), BF * 32, arena, st>>>(P);
-    PFZ_LAUNCH_OK();
-    return 0;
 }
 
 }  // namespace pfz
@@ -1143,9 +867,7 @@ int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, cons
     blk_perm_kernel<<<blk_grid(n_from + 1, 256, 148 * 16), 256, 0, st>>>(row_keys, a_indptr, n_from, perm, pos_ptr);
     PFZ_LAUNCH_OK();
     if (scan_exclusive_i32(pos_ptr, pos_ptr, (int64_t)n_from + 1, w + L.scan_ws, st)) return 1;
-    const char *env_v = getenv("PFZ_BLOCK_KERNEL");                // developer knob: 2 = the previous main kernel (kept for A/B runs)
-    const bool v2 = env_v && atoi(env_v) == 2;
-    const int row_stride = tile * (acc_bits == 16 ? 2 : 4) + (v2 ? 0 : 128);   // version 3: 32 dump words behind every row
+    const int row_stride = tile * (acc_bits == 16 ? 2 : 4) + 128;  // 32 dump words behind every row's cells
     if (block_rows == 4)
         blk_table_kernel<4><<<blk_grid((int64_t)n_groups * 32, 128, 148 * 16), 128, 0, st>>>(a_indptr, a_indices, a_data, n_from, perm, pos_ptr, row_stride,
                                                                                              blk_terms, blk_fvdesc, blk_fv, descs, n_groups, err_flag_dev);
@@ -1160,13 +882,17 @@ int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, cons
     BlockParams P{a_indptr, a_indices, a_data, n_from, perm, descs, 2 * n_groups, blk_terms, blk_fvdesc, blk_fv, seg,
                   reinterpret_cast<const uint2 *>(post_pk), b_indptr, b_indices, b_data, tile, n_tiles, n_to, k, min_similarity, self_match,
                   from_index_base, to_index_base, n_splits, top_idx, top_val, counters};
-    if (v2) {
-        PFZ_REQUIRE(block_rows != 4 && acc_bits == 32, "pfz_spcos_topk_block: the version-2 kernel has no 4-row variant and reads the q26 posting format");
-        if (acc_bits == 16) return block_rows == 8 ? launch_block<8, true>(P, n_groups, sms, smem_max, st) : launch_block<16, true>(P, n_groups, sms, smem_max, st);
-        return block_rows == 8 ? launch_block<8, false>(P, n_groups, sms, smem_max, st) : launch_block<16, false>(P, n_groups, sms, smem_max, st);
-    }
     if (block_rows == 4) return acc_bits == 16 ? launch_blk3<4, true>(P, n_groups, sms, smem_max, st) : launch_blk3<4, false>(P, n_groups, sms, smem_max, st);
     if (acc_bits == 16) return block_rows == 8 ? launch_blk3<8, true>(P, n_groups, sms, smem_max, st) : launch_blk3<16, true>(P, n_groups, sms, smem_max, st);
     return block_rows == 8 ? launch_blk3<8, false>(P, n_groups, sms, smem_max, st) : launch_blk3<16, false>(P, n_groups, sms, smem_max, st);
 }
+
+#ifdef PFZ_B3_TIMING
+int pfz_debug_b3_cycles(unsigned long long *out8, int32_t reset) {
+    PFZ_CUDA_OK(cudaDeviceSynchronize());
+    PFZ_CUDA_OK(cudaMemcpyFromSymbol(out8, g_b3_cycles, sizeof(unsigned long long) * 8));
+    if (reset) { unsigned long long z[8] = {0}; PFZ_CUDA_OK(cudaMemcpyToSymbol(g_b3_cycles, z, sizeof(z))); }
+    return 0;
+}
+#endif
 }

@@ -21,7 +21,10 @@ namespace pfz {
 constexpr double K2H_SCALE = 67108864.0;         // 2^26
 constexpr double K2H_MARGIN = 2e-5;              // >= 2 x (1.5 units x 256 terms x 2^-26) = 1.15e-5
 constexpr unsigned K2H_MARGIN_Q = 1343u;         // ceil(K2H_MARGIN * 2^26)
-constexpr int HASH_WARPS = 8, HASH_NT = HASH_WARPS * 32;
+#ifndef PFZ_HASH_WARPS
+#define PFZ_HASH_WARPS 4
+#endif
+constexpr int HASH_WARPS = PFZ_HASH_WARPS, HASH_NT = HASH_WARPS * 32;   // warps per CTA (= per from-row): 4 -> 8 CTAs per SM at 64 registers
 constexpr int HASH_TERM_CAP = 256;               // terms per from-row
 constexpr int HASH_ITEM_CAP = 128;
 constexpr int HASH_CQ = 384;                     // candidate queue
