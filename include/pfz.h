@@ -193,7 +193,7 @@ int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, cons
  * inputs where a from-row touches a small fraction of the to-rows (uniform text).  Same reference call site
  * (polyfuzz/models/_utils.py:82), bit-identical results.
  *   index: built with tile = 65536 (the largest the 16-bit local rows allow) + pfz_index_pack_q26; from-rows <= 256 terms.
- *   table_slots: 2048 | 8192 | 16384; a row whose postings exceed half the table is scored in several tile-range passes;
+ *   table_slots: 1024 | 2048 | 8192 | 16384; a row whose postings exceed half the table is scored in several tile-range passes;
  *   *err_flag_dev: 2 = table overflow (a single tile held more postings than the table), 3 = row longer than 256 terms.
  *   excl_val/excl_idx: as pfz_spcos_topk (paging).  Output [n_splits][n_from][k].                                        */
 int pfz_spcos_topk_hash(const int32_t *a_indptr, const int32_t *a_indices, const double *a_data, int32_t n_from, const int32_t *seg,

@@ -201,6 +201,7 @@ struct BlockParams {
     const int32_t *b_indptr; const int32_t *b_indices; const double *b_data;
     int tile, n_tiles, n_to, k; double min_sim; int self_match; int64_t from_base, to_base; int n_splits;
     int32_t *top_idx; double *top_val; int32_t *counter;
+    int32_t *glist; int32_t *gcnt; int gcap;
 };
 
 __device__ __forceinline__ unsigned sm_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -276,33 +277,33 @@ struct __align__(16) B3Item { int off; int cnt; unsigned fva; int nf; };
 struct __align__(16) B3Ctx {
     const int32_t *a_indptr; const int32_t *a_indices; const double *a_data;
     const int32_t *b_indptr; const int32_t *b_indices; const double *b_data;
-    int64_t to_base; double scale; int K; int T; int TW; int pad;
+    int64_t to_base; double scale; int K; int T; int TW; int gcap;
+    int32_t *glist; int64_t grow0;               // deferred candidates: list of row r at glist + (grow0 + r) * gcap (grow0 = split * n_from)
 };
 // filter / top-k state of one from-row (= one warp)
 struct __align__(16) B3Row {
     double tv[32]; int ti[32];                   // exact top-k list, lane r = rank r
     unsigned av[32];                             // the K largest fixed-point sums seen (lane r = r-th largest)
     int cand[B3_QCAP];                           // queued candidates (local to-row ids)
-    int row, self_loc, ncand; unsigned thr, akth, MQ, gate; int pad;
+    int row, self_loc, ncand; unsigned thr, akth, MQ, gate; int gcount;        // gcount: candidates already moved to the row's global list
 };
 
-// exact scoring + insertion of the queued candidates of one from-row (32 per round, newest first); raises thr to the K-th exact key
-__device__ __noinline__ void blk3_drain(const B3Ctx *cx, B3Row *rs) {
+// Exact scoring + insertion of a list of candidates (local to-row ids) of one from-row into its top-k list (tv / ti, lane r = rank r),
+// 32 candidates per round, newest first.  kv / ki: the K-th key on return.
+__device__ __forceinline__ void blk_exact_rounds(const int32_t *__restrict__ a_indptr, const int32_t *__restrict__ a_indices, const double *__restrict__ a_data,
+                                                 const int32_t *__restrict__ b_indptr, const int32_t *__restrict__ b_indices, const double *__restrict__ b_data,
+                                                 int64_t to_base, int K, int row, int self_loc, const int *cand, int ncand, double &tv, int &ti, double &kv, int &ki) {
     const int lane = threadIdx.x & 31;
-    const int K = cx->K, row = rs->row, self_loc = rs->self_loc;
-    const int32_t *__restrict__ b_indptr = cx->b_indptr;
-    const int a0 = cx->a_indptr[row], m = cx->a_indptr[row + 1] - a0;
-    int ncand = rs->ncand;
-    double tv = rs->tv[lane]; int ti = rs->ti[lane];
-    double kv = shfl_d(tv, K - 1); int ki = __shfl_sync(FULL, ti, K - 1);
+    const int a0 = a_indptr[row], m = a_indptr[row + 1] - a0;
+    kv = shfl_d(tv, K - 1); ki = __shfl_sync(FULL, ti, K - 1);
     while (ncand > 0) {
         const int n_round = min(32, ncand), off = ncand - n_round;
         double sc = 0.0; int j = -1; bool cnd = false;
         if (lane < n_round) {
-            const int jloc = rs->cand[off + lane];
+            const int jloc = cand[off + lane];
             const int b0 = b_indptr[jloc];
-            sc = blk_exact_dot(cx->a_indices + a0, cx->a_data + a0, m, cx->b_indices + b0, cx->b_data + b0, b_indptr[jloc + 1] - b0);
-            j = (int)(cx->to_base + jloc);
+            sc = blk_exact_dot(a_indices + a0, a_data + a0, m, b_indices + b0, b_data + b0, b_indptr[jloc + 1] - b0);
+            j = (int)(to_base + jloc);
             cnd = blk_key_before(sc, j, kv, ki) && jloc != self_loc;
         }
         unsigned cm = __ballot_sync(FULL, cnd);
@@ -323,6 +324,14 @@ __device__ __noinline__ void blk3_drain(const B3Ctx *cx, B3Row *rs) {
         }
         ncand = off;
     }
+}
+// in-kernel exact re-scoring of a row's queue (only when its global candidate list is full); raises thr to the K-th exact key
+__device__ __noinline__ void blk3_drain(const B3Ctx *cx, B3Row *rs) {
+    const int lane = threadIdx.x & 31;
+    double tv = rs->tv[lane]; int ti = rs->ti[lane];
+    double kv; int ki;
+    blk_exact_rounds(cx->a_indptr, cx->a_indices, cx->a_data, cx->b_indptr, cx->b_indices, cx->b_data, cx->to_base, cx->K, rs->row, rs->self_loc,
+                     rs->cand, rs->ncand, tv, ti, kv, ki);
     rs->tv[lane] = tv; rs->ti[lane] = ti;
     if (lane == 0) {
         rs->ncand = 0;
@@ -333,6 +342,20 @@ __device__ __noinline__ void blk3_drain(const B3Ctx *cx, B3Row *rs) {
         }
     }
     __syncwarp();
+}
+// The queue of a row moves to its list in global memory: the exact re-scoring of the whole list is a kernel of its own
+// (blk_exact_kernel: one warp per row, nothing else in its way) instead of 11 % of this kernel's warp time plus a barrier wait at
+// the end of every block.  A full list falls back to re-scoring here.
+__device__ __noinline__ void blk3_flush(const B3Ctx *cx, B3Row *rs) {
+    const int lane = threadIdx.x & 31;
+    const int ncand = rs->ncand, g = rs->gcount;
+    if (g + ncand <= cx->gcap) {
+        int32_t *dst = cx->glist + (size_t)(cx->grow0 + rs->row) * cx->gcap + g;
+        for (int q = lane; q < ncand; q += 32) dst[q] = rs->cand[q];
+        __syncwarp();
+        if (lane == 0) { rs->gcount = g + ncand; rs->ncand = 0; }
+        __syncwarp();
+    } else blk3_drain(cx, rs);
 }
 
 // largest accumulator of a 16-byte group: plain maximum, or the maximum over the 16-bit halves
@@ -396,10 +419,10 @@ __device__ __noinline__ unsigned blk3_extract(const B3Ctx *cx, B3Row *rs, unsign
             const bool take = x > gate;
             unsigned tm = __ballot_sync(FULL, take);
             if (tm == 0u) continue;
-            if (ncand + NC > B3_QCAP) {                               // queue full: re-score what is queued now
+            if (ncand + NC > B3_QCAP) {                               // queue full: move it to the row's global list
                 if (lane == 0) rs->ncand = ncand;
                 __syncwarp();
-                blk3_drain(cx, rs);
+                blk3_flush(cx, rs);
                 ncand = 0;
                 gate = max(gate, rs->thr);
             }
@@ -579,7 +602,8 @@ __global__ void __launch_bounds__(BF * 32, PFZ_B3_MIN_CTAS(BF)) spcos_blk3_kerne
     if (tid == 0) {
         cx->a_indptr = P.a_indptr; cx->a_indices = P.a_indices; cx->a_data = P.a_data;
         cx->b_indptr = P.b_indptr; cx->b_indices = P.b_indices; cx->b_data = P.b_data;
-        cx->to_base = P.to_base; cx->scale = P16 ? 32768.0 : K2B_SCALE; cx->K = P.k; cx->T = T; cx->TW = TW; cx->pad = 0;
+        cx->to_base = P.to_base; cx->scale = P16 ? 32768.0 : K2B_SCALE; cx->K = P.k; cx->T = T; cx->TW = TW; cx->gcap = P.gcap;
+        cx->glist = P.glist; cx->grow0 = (int64_t)blockIdx.y * P.n_from;
     }
     const unsigned acc_s = sm_u32(acc);
     const unsigned dump_s = acc_s + ((unsigned)(TW + lane) << 2);       // this lane's dump word of row 0
@@ -620,7 +644,7 @@ __global__ void __launch_bounds__(BF * 32, PFZ_B3_MIN_CTAS(BF)) spcos_blk3_kerne
                 const unsigned MQ = P16 ? (unsigned)(4 * m + 2) : K2B_MARGIN_Q;  // filter margin in accumulator units (16-bit: -1.01 < update - exact < 2.01)
                 const double y = fmax(P.min_sim, 0.0) * (P16 ? 32768.0 : K2B_SCALE) - (double)MQ;
                 const unsigned thr = y <= 0.0 ? 0u : (unsigned)__double2ll_rd(y);
-                rs->row = row; rs->self_loc = stau >= 0 ? stau * T + sjl : -1; rs->ncand = 0;
+                rs->row = row; rs->self_loc = stau >= 0 ? stau * T + sjl : -1; rs->ncand = 0; rs->gcount = 0;
                 rs->thr = thr; rs->akth = 0u; rs->MQ = MQ; rs->gate = thr;
                 wsum[w] = m;
             }
@@ -738,18 +762,43 @@ __global__ void __launch_bounds__(BF * 32, PFZ_B3_MIN_CTAS(BF)) spcos_blk3_kerne
         B3_TICK(4);
         if (has_row) {
             __syncwarp();
-            blk3_drain(cx, rs);
-            if (lane < P.k) {
-                const size_t o = ((size_t)split * P.n_from + rs->row) * P.k + lane;
+            blk3_flush(cx, rs);
+            const size_t ro = (size_t)split * P.n_from + rs->row;
+            if (lane < P.k) {                                          // the list as far as it was scored here (normally empty)
                 const int ti = rs->ti[lane];
-                P.top_idx[o] = ti;
-                P.top_val[o] = (ti >= 0) ? rs->tv[lane] : 0.0;
+                P.top_idx[ro * P.k + lane] = ti;
+                P.top_val[ro * P.k + lane] = (ti >= 0) ? rs->tv[lane] : 0.0;
             }
+            if (lane == 0) P.gcnt[ro] = rs->gcount;
         }
         B3_TICK(5);                                                       // exact re-scoring at the end of the block
         __syncthreads();
         B3_TICK(6);                                                       // wait at the end of the block
     }
+}
+
+// Exact re-scoring of every row's candidate list (deferred from the main kernel): one warp per (split, from-row).
+struct ExactParams {
+    const int32_t *a_indptr; const int32_t *a_indices; const double *a_data;
+    const int32_t *b_indptr; const int32_t *b_indices; const double *b_data;
+    const int32_t *glist; const int32_t *gcnt; int gcap; int n_from; int n_splits; int n_to; int k; double min_sim; int self_match;
+    int64_t from_base, to_base; int32_t *top_idx; double *top_val;
+};
+__global__ void __launch_bounds__(256) blk_exact_kernel(const ExactParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (gw >= (int64_t)P.n_splits * P.n_from) return;
+    const int n = P.gcnt[gw];
+    if (n == 0) return;                                             // the main kernel's list (empty slots: -1, 0) stands
+    const int row = (int)(gw % P.n_from), K = P.k;
+    const int64_t self_j = P.from_base + row - P.to_base;
+    const int self_loc = (P.self_match && self_j >= 0 && self_j < (int64_t)P.n_to) ? (int)self_j : -1;
+    double tv = P.min_sim; int ti = -1;
+    if (lane < K) { ti = P.top_idx[gw * K + lane]; if (ti >= 0) tv = P.top_val[gw * K + lane]; }
+    double kv; int ki;
+    blk_exact_rounds(P.a_indptr, P.a_indices, P.a_data, P.b_indptr, P.b_indices, P.b_data, P.to_base, K, row, self_loc,
+                     P.glist + (size_t)gw * P.gcap, n, tv, ti, kv, ki);
+    if (lane < K) { P.top_idx[gw * K + lane] = ti; P.top_val[gw * K + lane] = (ti >= 0) ? tv : 0.0; }
 }
 
 template <int BF, bool P16>
@@ -779,8 +828,9 @@ static int64_t pow2_at_least(int64_t n) { int64_t p = 2; while (p < n) p <<= 1; 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct BlockWs {
-    size_t term_keys, term_rank, row_keys, perm, pos_ptr, scan_ws, blk_terms, blk_fvdesc, blk_fv, descs, counters, total;
+    size_t term_keys, term_rank, row_keys, perm, pos_ptr, scan_ws, blk_terms, blk_fvdesc, blk_fv, descs, counters, gcnt, glist, total;
 };
+constexpr int B3_GCAP = 192;                     // deferred candidates per (split, from-row); beyond that the main kernel re-scores in place
 static BlockWs block_ws_layout(int64_t n_from, int64_t nnz_cap, int64_t n_vocab, int n_splits) {
     BlockWs L; size_t o = 0;
     const int64_t vp = pow2_at_least(n_vocab), np = pow2_at_least(n_from);
@@ -796,6 +846,8 @@ static BlockWs block_ws_layout(int64_t n_from, int64_t nnz_cap, int64_t n_vocab,
     L.blk_fv = o; o += align256((size_t)(nnz_cap + 1) * 8);
     L.descs = o; o += align256((size_t)(2 * n_groups + 1) * sizeof(BlockDesc));
     L.counters = o; o += align256((size_t)(n_splits + 1) * 4);
+    L.gcnt = o; o += align256((size_t)n_splits * (size_t)n_from * 4);
+    L.glist = o; o += align256((size_t)n_splits * (size_t)n_from * B3_GCAP * 4);
     L.total = o;
     return L;
 }
@@ -881,10 +933,20 @@ int pfz_spcos_topk_block(const int32_t *a_indptr, const int32_t *a_indices, cons
     PFZ_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t) * (size_t)n_splits, st));
     BlockParams P{a_indptr, a_indices, a_data, n_from, perm, descs, 2 * n_groups, blk_terms, blk_fvdesc, blk_fv, seg,
                   reinterpret_cast<const uint2 *>(post_pk), b_indptr, b_indices, b_data, tile, n_tiles, n_to, k, min_similarity, self_match,
-                  from_index_base, to_index_base, n_splits, top_idx, top_val, counters};
-    if (block_rows == 4) return acc_bits == 16 ? launch_blk3<4, true>(P, n_groups, sms, smem_max, st) : launch_blk3<4, false>(P, n_groups, sms, smem_max, st);
-    if (acc_bits == 16) return block_rows == 8 ? launch_blk3<8, true>(P, n_groups, sms, smem_max, st) : launch_blk3<16, true>(P, n_groups, sms, smem_max, st);
-    return block_rows == 8 ? launch_blk3<8, false>(P, n_groups, sms, smem_max, st) : launch_blk3<16, false>(P, n_groups, sms, smem_max, st);
+                  from_index_base, to_index_base, n_splits, top_idx, top_val, counters,
+                  reinterpret_cast<int32_t *>(w + L.glist), reinterpret_cast<int32_t *>(w + L.gcnt), B3_GCAP};
+    int rc;
+    if (block_rows == 4) rc = acc_bits == 16 ? launch_blk3<4, true>(P, n_groups, sms, smem_max, st) : launch_blk3<4, false>(P, n_groups, sms, smem_max, st);
+    else if (acc_bits == 16) rc = block_rows == 8 ? launch_blk3<8, true>(P, n_groups, sms, smem_max, st) : launch_blk3<16, true>(P, n_groups, sms, smem_max, st);
+    else rc = block_rows == 8 ? launch_blk3<8, false>(P, n_groups, sms, smem_max, st) : launch_blk3<16, false>(P, n_groups, sms, smem_max, st);
+    if (rc) return rc;
+    // exact re-scoring of the candidate lists the main kernel left behind
+    ExactParams E{a_indptr, a_indices, a_data, b_indptr, b_indices, b_data, P.glist, P.gcnt, B3_GCAP, n_from, n_splits, n_to, k, min_similarity,
+                  self_match, from_index_base, to_index_base, top_idx, top_val};
+    const int64_t n_warps = (int64_t)n_splits * n_from;
+    blk_exact_kernel<<<(unsigned)((n_warps + 7) / 8), 256, 0, st>>>(E);
+    PFZ_LAUNCH_OK();
+    return 0;
 }
 
 #ifdef PFZ_B3_TIMING

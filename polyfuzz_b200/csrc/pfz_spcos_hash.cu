@@ -85,8 +85,11 @@ __host__ __device__ inline size_t hash_arena_bytes() {
     return (size_t)H * 8 + (size_t)HASH_ITEM_CAP * 16 + (size_t)HASH_TERM_CAP * 8 + (size_t)HASH_CQ * 12 + 512;
 }
 
+#ifndef PFZ_HASH_MIN_CTAS
+#define PFZ_HASH_MIN_CTAS 8    // 64 registers per thread: without the bound ptxas spends 119 and 4 CTAs fit (22.6 vs 14.2 ms)
+#endif
 template <int H, int LOGH>
-__global__ void __launch_bounds__(HASH_NT) spcos_hash_kernel(const HashParams P) {
+__global__ void __launch_bounds__(HASH_NT, PFZ_HASH_MIN_CTAS) spcos_hash_kernel(const HashParams P) {
     extern __shared__ __align__(16) unsigned char dyn[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -350,7 +353,7 @@ int pfz_spcos_topk_hash(const int32_t *a_indptr, const int32_t *a_indices, const
     PFZ_REQUIRE(k >= 1 && k <= 32, "pfz_spcos_topk_hash: k=%d unsupported (1..32)", k);
     PFZ_REQUIRE(tile >= 64 && tile <= 65536, "pfz_spcos_topk_hash: tile %d out of range", tile);
     PFZ_REQUIRE(n_splits >= 1 && n_splits <= n_tiles, "pfz_spcos_topk_hash: n_splits %d out of range", n_splits);
-    PFZ_REQUIRE(table_slots == 2048 || table_slots == 8192 || table_slots == 16384, "pfz_spcos_topk_hash: table_slots %d must be 2048, 8192 or 16384", table_slots);
+    PFZ_REQUIRE(table_slots == 1024 || table_slots == 2048 || table_slots == 8192 || table_slots == 16384, "pfz_spcos_topk_hash: table_slots %d must be 1024, 2048, 8192 or 16384", table_slots);
     if (n_from <= 0) return 0;
     cudaStream_t st = as_stream(stream);
     int dev = 0, sms = 0, smem_max = 0;
@@ -361,6 +364,7 @@ int pfz_spcos_topk_hash(const int32_t *a_indptr, const int32_t *a_indices, const
     HashParams P{a_indptr, a_indices, a_data, n_from, seg, reinterpret_cast<const uint2 *>(post_pk), b_indptr, b_indices, b_data, tile, n_tiles,
                  n_to, k, min_similarity, self_match, from_index_base, to_index_base, n_splits, excl_val, excl_idx, top_idx, top_val, row_counter,
                  err_flag_dev};
+    if (table_slots == 1024) return launch_hash<1024, 10>(P, sms, smem_max, st);
     if (table_slots == 2048) return launch_hash<2048, 11>(P, sms, smem_max, st);
     if (table_slots == 8192) return launch_hash<8192, 13>(P, sms, smem_max, st);
     return launch_hash<16384, 14>(P, sms, smem_max, st);

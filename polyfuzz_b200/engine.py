@@ -62,7 +62,8 @@ class _PinnedPool:
             self.free.append((buf, ev))
 
 
-_PINNED = _PinnedPool()
+_PINNED = _PinnedPool()          # H2D staging
+_PINNED_OUT = _PinnedPool()      # result buffers of the frame tail (kept apart: a small H2D must never grab a 64 MB result buffer)
 
 
 def _to_dev(arr, dtype=None):

@@ -155,7 +155,7 @@ def assemble_matches_device(from_arrow, to_blob, to_off, top_idx, top_val) -> pd
     # D2H into a pooled pinned buffer (a pageable destination runs at ~4 GB/s and a fresh 35 MB host allocation costs ~8 ms of
     # page faults).  The frame's columns are zero-copy views of that buffer; it returns to the pool when the last view dies.
     import weakref
-    from ..engine import _PINNED
+    from ..engine import _PINNED_OUT as _PINNED
     dev_all = torch.cat(parts)
     nbytes = dev_all.numel()
     stage = _PINNED.take(nbytes)

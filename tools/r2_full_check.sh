@@ -13,4 +13,4 @@ try:
 except Exception as e: print("bench parse failed", e)
 PY
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --skip c3,c4,c5,e2e > gpurun_out/r2_launches_bench.log 2>&1
-timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:spcos_block_kernel -s 1 -c 1 -o gpurun_out/r2_k2_block -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --skip c3,c4,c5,e2e > gpurun_out/r2_ncu_block.log 2>&1; tail -2 gpurun_out/r2_ncu_block.log
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:spcos_blk3_kernel -s 1 -c 1 -o gpurun_out/r2_k2_blk3 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --skip c3,c4,c5,e2e > gpurun_out/r2_ncu_block.log 2>&1; tail -2 gpurun_out/r2_ncu_block.log
