@@ -390,60 +390,49 @@ __device__ __noinline__ unsigned blk3_first_gate(const B3Ctx *cx, const B3Row *r
     return gate;
 }
 
-// Candidates of one scan step (two 16-byte groups per lane: c_base + lane and c_base + 32 + lane; hl0 / hl1 = lanes whose group
-// holds a cell above the gate).  The groups are still in shared memory: for every flagged group the first lanes of the warp
-// read ONE cell each (a half-word in 16-bit mode), vote, queue the cells above the gate and keep the K largest sums; the
-// queue is re-scored exactly when it fills.  Returns the new gate.
-template <bool P16>
-__device__ __noinline__ unsigned blk3_extract(const B3Ctx *cx, B3Row *rs, unsigned row_s, int c_base, unsigned hl0, unsigned hl1, unsigned gate, int cell0) {
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const int K = cx->K, TW = cx->TW;
-    const unsigned MQ = rs->MQ;
-    unsigned av = rs->av[lane], akth = rs->akth;
-    int ncand = rs->ncand;
-    constexpr int NC = P16 ? 8 : 4;                                 // cells per 16-byte group
-#pragma unroll 1
-    for (int g = 0; g < 2; ++g) {
-        unsigned hl = g == 0 ? hl0 : hl1;
-#pragma unroll 1
-        while (hl) {
-            const int src = __ffs(hl) - 1; hl &= hl - 1;
-            const int grp = c_base + src + 32 * g;
-            unsigned x = 0u;
-            if (lane < NC) {
-                const unsigned a = row_s + ((unsigned)grp << 4);
-                if (P16) { unsigned short h; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a + 2u * (unsigned)lane)); x = h; }
-                else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(a + 4u * (unsigned)lane));
-            }
-            const bool take = x > gate;
-            unsigned tm = __ballot_sync(FULL, take);
-            if (tm == 0u) continue;
-            if (ncand + NC > B3_QCAP) {                               // queue full: move it to the row's global list
-                if (lane == 0) rs->ncand = ncand;
-                __syncwarp();
-                blk3_flush(cx, rs);
-                ncand = 0;
-                gate = max(gate, rs->thr);
-            }
-            if (take) rs->cand[ncand + __popc(tm & lt)] = cell0 + grp * 4 + (P16 ? (lane >> 1) + ((lane & 1) ? TW : 0) : lane);
-            ncand += __popc(tm);
-            while (tm) {
-                const int s2 = __ffs(tm) - 1; tm &= tm - 1;
-                const unsigned cx2 = __shfl_sync(FULL, x, s2);
-                if (cx2 <= akth) continue;
-                const int pos = __popc(__ballot_sync(FULL, (lane < K) && av >= cx2));
-                const unsigned up = __shfl_up_sync(FULL, av, 1);
-                if (lane > pos) av = up; else if (lane == pos) av = cx2;
-                akth = __shfl_sync(FULL, av, K - 1);
-            }
-            if (akth > MQ) gate = max(gate, akth - MQ);
-        }
-    }
-    rs->av[lane] = av;
-    if (lane == 0) { rs->akth = akth; rs->ncand = ncand; rs->gate = gate; }
+// Filter state of a row while candidates are taken: registers of blk3_scan_slow for the whole row scan
+struct B3St { unsigned av, akth, gate, MQ; int ncand; };
+__device__ __forceinline__ B3St blk3_load_state(const B3Row *rs, int lane, unsigned gate) {
+    B3St st; st.av = rs->av[lane]; st.akth = rs->akth; st.gate = gate; st.MQ = rs->MQ; st.ncand = rs->ncand; return st;
+}
+__device__ __forceinline__ void blk3_store_state(B3Row *rs, const B3St &st, int lane) {
+    rs->av[lane] = st.av;
+    if (lane == 0) { rs->akth = st.akth; rs->ncand = st.ncand; rs->gate = st.gate; }
     __syncwarp();
-    return gate;
+}
+// One 16-byte group of accumulators at shared address `a` whose first cell is to-row `cellbase` and which holds a cell above
+// the gate: the first lanes of the warp read ONE cell each (a half-word in 16-bit mode), vote, queue the cells above the gate
+// and keep the K largest sums; a full queue moves to the row's global list.
+template <bool P16>
+__device__ __forceinline__ void blk3_take_group(const B3Ctx *cx, B3Row *rs, B3St &st, unsigned a, int cellbase, int lane, int K, int TW) {
+    constexpr int NC = P16 ? 8 : 4;                                 // cells per 16-byte group
+    unsigned x = 0u;
+    if (lane < NC) {
+        if (P16) { unsigned short h; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a + 2u * (unsigned)lane)); x = h; }
+        else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(a + 4u * (unsigned)lane));
+    }
+    const bool take = x > st.gate;
+    unsigned tm = __ballot_sync(FULL, take);
+    if (tm == 0u) return;
+    if (st.ncand + NC > B3_QCAP) {                               // queue full: move it to the row's global list
+        if (lane == 0) rs->ncand = st.ncand;
+        __syncwarp();
+        blk3_flush(cx, rs);
+        st.ncand = 0;
+        st.gate = max(st.gate, rs->thr);
+    }
+    if (take) rs->cand[st.ncand + __popc(tm & ((1u << lane) - 1u))] = cellbase + (P16 ? (lane >> 1) + ((lane & 1) ? TW : 0) : lane);
+    st.ncand += __popc(tm);
+    while (tm) {
+        const int s2 = __ffs(tm) - 1; tm &= tm - 1;
+        const unsigned cx2 = __shfl_sync(FULL, x, s2);
+        if (cx2 <= st.akth) continue;
+        const int pos = __popc(__ballot_sync(FULL, (lane < K) && st.av >= cx2));
+        const unsigned up = __shfl_up_sync(FULL, st.av, 1);
+        if (lane > pos) st.av = up; else if (lane == pos) st.av = cx2;
+        st.akth = __shfl_sync(FULL, st.av, K - 1);
+    }
+    if (st.akth > st.MQ) st.gate = max(st.gate, st.akth - st.MQ);
 }
 
 // one posting chunk applied to the from-rows that hold the term (nf is warp-uniform); idle lanes (pk = 0) add into their dump word.
@@ -518,7 +507,7 @@ __device__ __noinline__ void blk3_item_loop(unsigned items_s, int total, const u
 
 // Scan + clear of one row.  The hot loop is a LEAF function (a call inside a loop makes ptxas keep the loop state in local
 // memory): it clears 16-byte groups (two per lane and step) until one holds a cell above the gate, which it leaves in place
-// and reports; the caller hands that step to blk3_extract and resumes.
+// and reports; the caller (blk3_scan_slow) takes the candidates of that step and resumes.
 template <bool P16>
 __device__ __noinline__ int blk3_scan_until_hit(unsigned row_s, int c, int ng, unsigned gate) {
 #pragma unroll 1
@@ -539,25 +528,36 @@ template <bool P16>
 __device__ __noinline__ void blk3_scan_slow(const B3Ctx *cx, B3Row *rs, unsigned row_s, int cell0, int c, int first) {
     const int lane = threadIdx.x & 31;
     const int ng = cx->TW >> 2;                                    // 16-byte groups of the row (a multiple of 32)
-    unsigned gate = rs->gate;
+    const int K = cx->K, TW = cx->TW;
+    B3St st = blk3_load_state(rs, lane, rs->gate);                 // the filter state stays in registers for the whole row
     if (first) {
-        gate = blk3_first_gate<P16>(cx, rs, row_s);
-        c = blk3_scan_until_hit<P16>(row_s, lane, ng, gate);
+        st.gate = blk3_first_gate<P16>(cx, rs, row_s);
+        c = blk3_scan_until_hit<P16>(row_s, lane, ng, st.gate);
     }
     while (c < ng) {
+        // the step at c holds a cell above the gate (two 16-byte groups per lane: c and c + 32)
         const unsigned a = row_s + ((unsigned)c << 4);
         const bool two = c + 32 < ng;
         const uint4 v0 = lds128(a);
         uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
         if (two) v1 = lds128(a + 512u);
-        const unsigned hl0 = __ballot_sync(FULL, blk3_wmax<P16>(v0) > gate), hl1 = __ballot_sync(FULL, blk3_wmax<P16>(v1) > gate);
-        gate = blk3_extract<P16>(cx, rs, row_s, c - lane, hl0, hl1, gate, cell0);
+        const unsigned hl0 = __ballot_sync(FULL, blk3_wmax<P16>(v0) > st.gate), hl1 = __ballot_sync(FULL, blk3_wmax<P16>(v1) > st.gate);
+        const int c_base = c - lane;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+            unsigned hl = g == 0 ? hl0 : hl1;
+#pragma unroll 1
+            while (hl) {
+                const int src = __ffs(hl) - 1; hl &= hl - 1;
+                const int grp = c_base + src + 32 * g;
+                blk3_take_group<P16>(cx, rs, st, row_s + ((unsigned)grp << 4), cell0 + grp * 4, lane, K, TW);
+            }
+        }
         sts128_zero(a);
         if (two) sts128_zero(a + 512u);
-        c = blk3_scan_until_hit<P16>(row_s, c + 64, ng, gate);
+        c = blk3_scan_until_hit<P16>(row_s, c + 64, ng, st.gate);
     }
-    if (lane == 0) rs->gate = gate;
-    __syncwarp();
+    blk3_store_state(rs, st, lane);
 }
 
 template <int BF, bool P16>
