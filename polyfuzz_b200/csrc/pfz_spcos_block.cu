@@ -525,15 +525,18 @@ __device__ __noinline__ int blk3_scan_until_hit(unsigned row_s, int c, int ng, u
 }
 // The rest of a row scan once a step holds a cell above the gate (or while fewer than K sums have been seen: first != 0).
 template <bool P16>
-__device__ __noinline__ void blk3_scan_slow(const B3Ctx *cx, B3Row *rs, unsigned row_s, int cell0, int c, int first) {
+__device__ __noinline__ void blk3_scan_row(const B3Ctx *cx, B3Row *rs, unsigned row_s, int cell0) {
     const int lane = threadIdx.x & 31;
     const int ng = cx->TW >> 2;                                    // 16-byte groups of the row (a multiple of 32)
-    const int K = cx->K, TW = cx->TW;
-    B3St st = blk3_load_state(rs, lane, rs->gate);                 // the filter state stays in registers for the whole row
-    if (first) {
-        st.gate = blk3_first_gate<P16>(cx, rs, row_s);
-        c = blk3_scan_until_hit<P16>(row_s, lane, ng, st.gate);
+    unsigned gate0 = rs->gate;
+    if (rs->akth == 0u) gate0 = blk3_first_gate<P16>(cx, rs, row_s);
+    int c = blk3_scan_until_hit<P16>(row_s, lane, ng, gate0);
+    if (c >= ng) {                                                 // the common case: nothing above the gate in this tile
+        if (gate0 != rs->gate) { if (lane == 0) rs->gate = gate0; __syncwarp(); }
+        return;
     }
+    const int K = cx->K, TW = cx->TW;
+    B3St st = blk3_load_state(rs, lane, gate0);                    // the filter state stays in registers for the rest of the row
     while (c < ng) {
         // the step at c holds a cell above the gate (two 16-byte groups per lane: c and c + 32)
         const unsigned a = row_s + ((unsigned)c << 4);
@@ -685,10 +688,8 @@ __global__ void __launch_bounds__(BF * 32, PFZ_B3_MIN_CTAS(BF)) spcos_blk3_kerne
             // ---- table phase: one work item per 32 postings of a (term, tile) segment ----
             auto emit = [&](int s, int len, unsigned fva, int nf) {
                 const int nch = (len + 31) >> 5;
-                const int incl = warp_incl_scan(nch);
                 int first = 0;
-                if (lane == 31 && incl > 0) first = atomicAdd(&icnt[par], incl);
-                first = __shfl_sync(FULL, first, 31) + incl - nch;
+                if (nch > 0) first = atomicAdd(&icnt[par], nch);         // (a handful of lanes per warp hold a term: cheaper than a warp scan)
                 if (nch > 0 && first < B3_ICAP) { B3Item it; it.off = s; it.cnt = len; it.fva = fva; it.nf = nf; items[first] = it; }
                 unsigned big = __ballot_sync(FULL, nch > 1);
                 while (big) {                                             // the further chunks of long segments: written by the whole warp
@@ -751,12 +752,7 @@ __global__ void __launch_bounds__(BF * 32, PFZ_B3_MIN_CTAS(BF)) spcos_blk3_kerne
                     }
                     __syncwarp();
                 }
-                const unsigned row_s = acc_s + (unsigned)(w * RW) * 4u;
-                if (rs->akth == 0u) blk3_scan_slow<P16>(cx, rs, row_s, tau * T, 0, 1);
-                else {
-                    const int c = blk3_scan_until_hit<P16>(row_s, lane, TW >> 2, rs->gate);
-                    if (c < (TW >> 2)) blk3_scan_slow<P16>(cx, rs, row_s, tau * T, c, 0);
-                }
+                blk3_scan_row<P16>(cx, rs, acc_s + (unsigned)(w * RW) * 4u, tau * T);
             }
         }
         B3_TICK(4);
