@@ -586,7 +586,8 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": data_kind, "config": config_dict(n, world, data_kind),
-            "k2": {"tile": result["index"].tile, "variant": variant, "V": vec.n_vocab, "nnz": nnz},
+            "k2": {"tile": result["index"].tile, "variant": variant, "V": vec.n_vocab, "nnz": nnz,
+                   "acc_bits": getattr(result["index"], "acc_bits", None), "block_rows": engine.BLOCK_ROWS if variant == "block" else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "step_ms_each": [round(x, 3) for x in step_ms], "step_ms_median": med,
             "step_outliers_over_5pct": int(sum(1 for x in step_ms if x > 1.05 * med)),

@@ -270,7 +270,10 @@ __device__ __forceinline__ unsigned warp_sort_desc_u32(unsigned x, int lane) {
 #endif
 constexpr int B3_ICAP_PER_ROW = PFZ_B3_ICAP_PER_ROW;              // staged work items per unit = 64 x block rows; larger units walk the term table directly
 constexpr int B3_QCAP = 128;                     // candidates a from-row may queue before they are re-scored exactly
-constexpr int B3_DEPTH = 3;                      // posting chunks in flight per warp
+#ifndef PFZ_B3_DEPTH
+#define PFZ_B3_DEPTH 3
+#endif
+constexpr int B3_DEPTH = PFZ_B3_DEPTH;                      // posting chunks in flight per warp
 
 struct __align__(16) B3Item { int off; int cnt; unsigned fva; int nf; };
 // what the rare paths need of the kernel parameters (one copy per CTA in shared memory)
