@@ -783,9 +783,16 @@ struct ExactParams {
     const int32_t *glist; const int32_t *gcnt; int gcap; int n_from; int n_splits; int n_to; int k; double min_sim; int self_match;
     int64_t from_base, to_base; int32_t *top_idx; double *top_val;
 };
+constexpr int EX_ROW_CAP = 128;                  // from-row terms staged in shared memory (the block kernel's contract; longer rows take the generic merge)
 __global__ void __launch_bounds__(256) blk_exact_kernel(const ExactParams P) {
-    const int lane = threadIdx.x & 31;
-    const int64_t gw = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    // The from-row is staged once per warp in shared memory; every lane scores one candidate: it walks ITS to-row (entries loaded
+    // four at a time, independent loads) and finds each term in the from-row by binary search -- the same number of steps in every
+    // lane, so the warp does not diverge as it does in a two-pointer merge.  Common terms are met in ascending order and the
+    // products are rounded before the add: the canonical fp64 score, bit for bit.
+    __shared__ int s_ai[8][EX_ROW_CAP];
+    __shared__ double s_av[8][EX_ROW_CAP];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * 8 + wl;
     if (gw >= (int64_t)P.n_splits * P.n_from) return;
     const int n = P.gcnt[gw];
     if (n == 0) return;                                             // the main kernel's list (empty slots: -1, 0) stands
@@ -795,8 +802,57 @@ __global__ void __launch_bounds__(256) blk_exact_kernel(const ExactParams P) {
     double tv = P.min_sim; int ti = -1;
     if (lane < K) { ti = P.top_idx[gw * K + lane]; if (ti >= 0) tv = P.top_val[gw * K + lane]; }
     double kv; int ki;
-    blk_exact_rounds(P.a_indptr, P.a_indices, P.a_data, P.b_indptr, P.b_indices, P.b_data, P.to_base, K, row, self_loc,
-                     P.glist + (size_t)gw * P.gcap, n, tv, ti, kv, ki);
+    const int a0 = P.a_indptr[row], m = P.a_indptr[row + 1] - a0;
+    const int32_t *cand = P.glist + (size_t)gw * P.gcap;
+    if (m > EX_ROW_CAP) {
+        blk_exact_rounds(P.a_indptr, P.a_indices, P.a_data, P.b_indptr, P.b_indices, P.b_data, P.to_base, K, row, self_loc, cand, n, tv, ti, kv, ki);
+    } else {
+        int *ai = s_ai[wl]; double *av = s_av[wl];
+        for (int e = lane; e < m; e += 32) { ai[e] = P.a_indices[a0 + e]; av[e] = P.a_data[a0 + e]; }
+        __syncwarp();
+        int steps = 0;
+        while ((1 << steps) <= m) ++steps;                           // binary-search steps for m entries: ceil(log2(m + 1))
+        kv = shfl_d(tv, K - 1); ki = __shfl_sync(FULL, ti, K - 1);
+        int left = n;
+        while (left > 0) {
+            const int n_round = min(32, left), off = left - n_round;    // newest first
+            double sc = 0.0; int j = -1; bool cnd = false;
+            if (lane < n_round) {
+                const int jloc = cand[off + lane];
+                const int b0 = P.b_indptr[jloc], b1 = P.b_indptr[jloc + 1];
+                for (int q = b0; q < b1; q += 4) {
+                    int t[4]; double wgt[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { t[u] = 0x7fffffff; wgt[u] = 0.0; if (q + u < b1) { t[u] = P.b_indices[q + u]; wgt[u] = P.b_data[q + u]; } }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        int lo = 0, hi = m;
+                        for (int st = 0; st < steps; ++st) { const int mid = (lo + hi) >> 1; if (lo < hi) { if (ai[mid] < t[u]) lo = mid + 1; else hi = mid; } }
+                        if (lo < m && ai[lo] == t[u]) sc = __dadd_rn(sc, __dmul_rn(av[lo], wgt[u]));
+                    }
+                }
+                j = (int)(P.to_base + jloc);
+                cnd = blk_key_before(sc, j, kv, ki) && jloc != self_loc;
+            }
+            unsigned cm = __ballot_sync(FULL, cnd);
+            while (cm) {
+                const int src = __ffs(cm) - 1;
+                const double cs = shfl_d(sc, src);
+                const int cj = __shfl_sync(FULL, j, src);
+                const bool stays = (lane < K) && blk_key_before(tv, ti, cs, cj);
+                const int pos = __popc(__ballot_sync(FULL, stays));
+                const double uv = __shfl_up_sync(FULL, tv, 1);
+                const int ui = __shfl_up_sync(FULL, ti, 1);
+                if (lane > pos) { tv = uv; ti = ui; }
+                else if (lane == pos) { tv = cs; ti = cj; }
+                kv = shfl_d(tv, K - 1);
+                ki = __shfl_sync(FULL, ti, K - 1);
+                cnd = cnd && lane != src && blk_key_before(sc, j, kv, ki);
+                cm = __ballot_sync(FULL, cnd);
+            }
+            left = off;
+        }
+    }
     if (lane < K) { P.top_idx[gw * K + lane] = ti; P.top_val[gw * K + lane] = (ti >= 0) ? tv : 0.0; }
 }
 
