@@ -137,7 +137,10 @@ class ClockSampler:
     showed up as +4 ms outliers in 14 ms steps.  Falls back to nvidia-smi if NVML is unavailable."""
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, recording=True):
+        # recording=False: the sampler thread (NVML init, first queries) starts during the warm-up and only records once
+        # `recording` is set -- starting it right before the timed region cost rank 0 tens of ms in the first timed steps at N = 8
+        self.recording = recording
         self.samples, self.maxs, self.reasons = [], [], set()
         self._stop = threading.Event()
         self.thread = None
@@ -158,11 +161,13 @@ class ClockSampler:
         nv = self.nv
         while not self._stop.is_set():
             try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                for name, bit in self.REASONS.items():
-                    if bits & bit:
-                        self.reasons.add(name)
+                if self.recording:
+                    self.samples.append(mhz)
+                    for name, bit in self.REASONS.items():
+                        if bits & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
             self._stop.wait(0.05)
@@ -361,10 +366,12 @@ def sub_c5(args, dev, rank, local_rank, world, comm, barrier, flush, peak):
         idx, val, csr_to, index = tfidf_topk_sharded(vec, s_from, s_to, lo, TOP_N, 0.0, self_match=False, fit=True, fit_on_from=True,
                                                      comm=comm, timings=k2_events if rec else None)
         res.update(idx=idx, val=val, vec=vec, csr=csr_to, index=index)
+    sampler = ClockSampler(local_rank, recording=False) if rank == 0 else None
     for _ in range(2):
         flush.zero_(); step(False)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.recording = True
     ms = []
     for _ in range(3):
         flush.zero_(); barrier()
@@ -453,11 +460,14 @@ def run_b200(args):
         result["idx"], result["val"], result["vec"], result["csr"], result["index"] = idx, val, vec, csr_to, index
 
     import gc
-    for _ in range(args.warmup):
-        flush.zero_(); device_step(False)
+    sampler = ClockSampler(local_rank, recording=False) if rank == 0 else None
+    for _ in range(args.warmup + (2 if world > 1 else 0)):   # same code path as the timed steps (event creation included); N > 1 gets two
+        flush.zero_(); barrier(); device_step(True)          # more untimed steps: the first collectives of a process are slow
     barrier()
+    k2_events.clear(); k1_events.clear()
     gc.collect(); gc.disable()                               # no collector pauses inside the timed steps
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.recording = True
     launches0 = _lib.launch_count()
     step_ms = []
     for _ in range(args.steps):
