@@ -364,7 +364,7 @@ def sub_c5(args, dev, rank, local_rank, world, comm, barrier, flush, peak):
     def step(rec):
         vec = engine.NgramTfidf((3, 3), True, True)
         idx, val, csr_to, index = tfidf_topk_sharded(vec, s_from, s_to, lo, TOP_N, 0.0, self_match=False, fit=True, fit_on_from=True,
-                                                     comm=comm, timings=k2_events if rec else None)
+                                                     comm=comm, timings=k2_events if rec else None, n_docs_total=2 * n)
         res.update(idx=idx, val=val, vec=vec, csr=csr_to, index=index)
     sampler = ClockSampler(local_rank, recording=False) if rank == 0 else None
     for _ in range(2):
@@ -456,7 +456,7 @@ def run_b200(args):
         idx, val, csr_to, index = tfidf_topk_sharded(vec, staged_from, staged_to, rank * n, TOP_N, 0.0, self_match=True,
                                                      from_index_base=0, fit=True, fit_on_from=False, comm=comm,
                                                      timings=k2_events if record_k2 else None,
-                                                     k1_timings=k1_events if record_k2 else None)
+                                                     k1_timings=k1_events if record_k2 else None, n_docs_total=n * world)
         result["idx"], result["val"], result["vec"], result["csr"], result["index"] = idx, val, vec, csr_to, index
 
     import gc

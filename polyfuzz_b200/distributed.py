@@ -136,8 +136,10 @@ def get_comm(group=None):
 
 def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, top_n, min_similarity,
                        self_match, from_index_base=0, fit=True, fit_on_from=True, comm=None, index=None,
-                       tile=None, timings=None, k1_timings=None):
+                       tile=None, timings=None, k1_timings=None, n_docs_total=None):
     """Sharded TF-IDF top-k.  Every rank passes the same from-list and its own to-shard.
+    n_docs_total: the number of documents the fit counts over ALL ranks (to-rows of every shard + the from-list when
+    fit_on_from), when the caller knows it -- saves one small all-reduce and a host sync per fit.
     Returns (top_idx[n_from,k] GLOBAL indices, top_val[n_from,k], csr_to_shard, index)."""
     from . import engine
     ev1 = None
@@ -149,10 +151,10 @@ def tfidf_topk_sharded(vectorizer, staged_from, staged_to_shard, to_index_base, 
         staged = [staged_to_shard, staged_from]
         same = staged_from is staged_to_shard           # single-GPU self-match: one matrix for both sides
         if same:                                        # (polyfuzz/models/_tfidf.py:114-116)
-            (rows_to,) = vectorizer.fit_staged([staged_to_shard], comm=comm)
+            (rows_to,) = vectorizer.fit_staged([staged_to_shard], comm=comm, n_docs_total=n_docs_total)
             rows_from = rows_to
         else:
-            rows_to, rows_from = vectorizer.fit_staged(staged, counted=counted, comm=comm)
+            rows_to, rows_from = vectorizer.fit_staged(staged, counted=counted, comm=comm, n_docs_total=n_docs_total)
         csr_to = vectorizer.emit(rows_to)
         index = engine.SparseIndex(csr_to, tile=tile, variant=engine.choose_variant(vectorizer.density(), vectorizer.max_row_nnz, csr_to.n_rows))
         csr_from = csr_to if same else vectorizer.emit(rows_from)

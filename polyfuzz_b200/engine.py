@@ -290,7 +290,7 @@ class NgramTfidf:
         _tfidf.py:109).  Returns the stage-A rows of each list so transform need not redo them."""
         return self.fit_staged([self.stage(l) for l in lists])
 
-    def fit_staged(self, staged, counted=None, comm=None):
+    def fit_staged(self, staged, counted=None, comm=None, n_docs_total=None):
         """Fit on device-resident lists.  Multi-GPU (comm given): `counted[i]` says whether list i
         contributes to df / n_docs on THIS rank (a replicated list is counted on rank 0 only); the
         dense df table and the document count are summed across ranks (one all-reduce), after which
@@ -312,9 +312,14 @@ class NgramTfidf:
         if comm is not None:
             if cs > DENSE_CODE_SPACE_MAX:
                 raise NotImplementedError("multi-GPU fit needs an n-gram code space <= 2^24 (e.g. cleaned n <= 4)")
-            meta = torch.tensor([n_docs, total_cap], dtype=torch.int64, device=dev)
-            comm.all_reduce_sum(meta)
-            n_docs, total_cap_all = int(meta[0].item()), int(meta[1].item())
+            if n_docs_total is not None:
+                # the caller knows the global document count (every rank sees the list lengths): no collective, no host sync here;
+                # the vocabulary buffers are then sized by the code space instead of the summed n-gram slots
+                n_docs, total_cap_all = int(n_docs_total), cs
+            else:
+                meta = torch.tensor([n_docs, total_cap], dtype=torch.int64, device=dev)
+                comm.all_reduce_sum(meta)
+                n_docs, total_cap_all = int(meta[0].item()), int(meta[1].item())
         else:
             total_cap_all = total_cap
         if total_cap_all == 0:

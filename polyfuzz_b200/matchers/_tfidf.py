@@ -193,7 +193,8 @@ class TFIDF(BaseMatcher):
             staged_to = None
         idx, val, csr_to, index = tfidf_topk_sharded(vec, staged_from, staged_to, lo, top_n, self._threshold(),
                                                      self_match, from_base, fit=re_train, fit_on_from=bool(to_list), comm=comm,
-                                                     index=self._index)
+                                                     index=self._index,
+                                                     n_docs_total=len(full_to) + (len(from_list) if to_list else 0))
         if re_train:
             self.tf_idf_to = csr_to
         self._index = index                                  # also when a transform had to fall back to the fp64 kernel
