@@ -166,17 +166,18 @@ int pfz_spcos_topk(const int32_t *a_indptr, const int32_t *a_indices, const doub
                    int32_t *top_idx, double *top_val, int32_t *row_counter, int32_t variant, void *stream);
 
 /* PFZ_K2_BLOCK -- from-row-block variant of K2 (csrc/pfz_spcos_block.cu): the from-rows are clustered by their heaviest
- * terms and scored block_rows (8 or 16) at a time by one CTA, so one load of a posting chunk serves every row of the block
- * that contains the term; 32-bit fixed-point sums in shared memory (red.shared.add.u32) filter, flagged cells are re-scored
- * exactly from the two CSR rows (as PFZ_K2_DENSE32): indices and scores are bit-identical to the other variants.  Same
- * reference call site (polyfuzz/models/_utils.py:82).
+ * terms and scored block_rows (4, 8 or 16) at a time by one CTA, so one load of a posting chunk serves every row of the block
+ * that contains the term; fixed-point sums in shared memory (red.shared.add.u32) filter, the to-rows whose sum passes a row's
+ * gate are listed in the workspace and re-scored exactly from the two CSR rows by a second kernel (as PFZ_K2_DENSE32): indices
+ * and scores are bit-identical to the other variants.  Same reference call site (polyfuzz/models/_utils.py:82).
  *   post_pk: uint2[nnz] in segment order of an index built with PFZ_INDEX_BANK_ORDER32: acc_bits 32: {tile-local row,
  *            round(weight * 2^26)} (pfz_index_pack_q26); acc_bits 16: {accumulator word byte offset | half-word selector << 16,
- *            max(1, round(weight * 2^15))} (pfz_index_pack_q15 with the same tile); tile: multiple of 128; k <= 32; from-rows <= 128 terms each (*err_flag_dev is set to 1
- *            otherwise); n_from < 2^22.
- *   acc_bits: 32 (one fixed-point accumulator per word, unit 2^-26) or 16 (two per word, unit 2^-15: twice the tile in the same
- *            shared memory, coarser filter; tile must be a multiple of 256).
- *   nnz_cap_from: capacity of a_indices / a_data (>= nnz).  ws: >= pfz_spcos_block_ws_bytes(...) bytes.
+ *            max(1, round(weight * 2^15))} (pfz_index_pack_q15 with the same tile).
+ *   tile: multiple of 128 in 128..4096; k <= 32; from-rows <= 128 terms each (*err_flag_dev is set to 1 otherwise); n_from < 2^22.
+ *   acc_bits: 16 (two fixed-point accumulators per word, unit 2^-15: twice the tile in the same shared memory, filter margin
+ *            4 m + 2 units for a from-row of m terms; tile must be a multiple of 256) or 32 (one per word, unit 2^-26, margin 1e-5).
+ *   nnz_cap_from: capacity of a_indices / a_data (>= nnz).  ws: >= pfz_spcos_block_ws_bytes(...) bytes (clustering keys, block
+ *            tables, and 192 candidate slots per (split, from-row)).
  *   Output as pfz_spcos_topk: [n_splits][n_from][k] partial lists (pfz_topk_merge when n_splits > 1).                    */
 int64_t pfz_spcos_block_ws_bytes(int32_t n_from, int64_t nnz_cap_from, int32_t n_vocab, int32_t n_splits);
 int pfz_index_pack_q26(const uint16_t *post_idx, const double *post_val, const int32_t *nnz_dev, void *post_pk, void *stream);
