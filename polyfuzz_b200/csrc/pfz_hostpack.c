@@ -67,7 +67,68 @@ static PyObject *hp_fill(PyObject *self, PyObject *args) {
     Py_RETURN_NONE;
 }
 
+/* fill_ascii(list, blob, offsets) -> total bytes, or -1: ONE pass for the common case -- a pure-ASCII list that fits the byte
+ * buffer the caller guessed (blob: writable bytes, offsets: writable int64[n + 1]).  -1 (a non-ASCII string or the buffer too
+ * small; nothing useful written) sends the caller to scan() + fill().  TypeError on a non-str element. */
+static PyObject *hp_fill_ascii(PyObject *self, PyObject *args) {
+    (void)self;
+    PyObject *lst; Py_buffer blob, offs;
+    if (!PyArg_ParseTuple(args, "Ow*w*", &lst, &blob, &offs)) return NULL;
+    if (!PyList_Check(lst) && !PyTuple_Check(lst)) { PyBuffer_Release(&blob); PyBuffer_Release(&offs); PyErr_SetString(PyExc_TypeError, "expected a list or tuple of str"); return NULL; }
+    PyObject *fast = PySequence_Fast(lst, "expected a sequence");
+    if (!fast) { PyBuffer_Release(&blob); PyBuffer_Release(&offs); return NULL; }
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
+    PyObject **items = PySequence_Fast_ITEMS(fast);
+    long long pos = 0; int ok = offs.len >= (Py_ssize_t)((n + 1) * 8), bad_type = 0;
+    if (ok) {
+        int64_t *o = (int64_t *)offs.buf;
+        uint8_t *dst = (uint8_t *)blob.buf;
+        const long long cap = blob.len;
+        o[0] = 0;
+        for (Py_ssize_t i = 0; i < n; ++i) {
+            PyObject *s = items[i];
+            if (!PyUnicode_Check(s)) { bad_type = 1; ok = 0; break; }
+            if (!PyUnicode_IS_ASCII(s)) { ok = 0; break; }
+            const Py_ssize_t len = PyUnicode_GET_LENGTH(s);
+            if (pos + len > cap) { ok = 0; break; }
+            memcpy(dst + pos, PyUnicode_DATA(s), (size_t)len);
+            pos += len;
+            o[i + 1] = pos;
+        }
+    }
+    Py_DECREF(fast); PyBuffer_Release(&blob); PyBuffer_Release(&offs);
+    if (bad_type) { PyErr_SetString(PyExc_TypeError, "all elements of the string list must be str"); return NULL; }
+    return PyLong_FromLongLong(ok ? pos : -1);
+}
+
+/* slots(offsets, slots_out, occ_out, lo, hi): per string the upper bound of its n-gram occurrences, sum_n max(0, len - n + 1)
+ * for n in lo..hi, and the exclusive prefix of those bounds (n + 1 entries) -- one pass instead of numpy's five. */
+static PyObject *hp_slots(PyObject *self, PyObject *args) {
+    (void)self;
+    Py_buffer offs, slots, occ; int lo, hi;
+    if (!PyArg_ParseTuple(args, "y*w*w*ii", &offs, &slots, &occ, &lo, &hi)) return NULL;
+    const Py_ssize_t n = offs.len / 8 - 1;
+    int ok = n >= 0 && slots.len >= n * 8 && occ.len >= (n + 1) * 8 && lo >= 1 && hi >= lo;
+    if (ok) {
+        const int64_t *o = (const int64_t *)offs.buf;
+        int64_t *sl = (int64_t *)slots.buf, *oc = (int64_t *)occ.buf;
+        int64_t acc = 0;
+        oc[0] = 0;
+        for (Py_ssize_t i = 0; i < n; ++i) {
+            const int64_t len = o[i + 1] - o[i];
+            int64_t v = 0;
+            for (int g = lo; g <= hi; ++g) { const int64_t c = len - g + 1; if (c > 0) v += c; }
+            sl[i] = v; acc += v; oc[i + 1] = acc;
+        }
+    }
+    PyBuffer_Release(&offs); PyBuffer_Release(&slots); PyBuffer_Release(&occ);
+    if (!ok) { PyErr_SetString(PyExc_ValueError, "pfz_hostpack.slots: buffers do not match"); return NULL; }
+    Py_RETURN_NONE;
+}
+
 static PyMethodDef methods[] = {
+    {"slots", hp_slots, METH_VARARGS, "slots(offsets, slots_out, occ_out, lo, hi)"},
+    {"fill_ascii", hp_fill_ascii, METH_VARARGS, "fill_ascii(list, blob, offsets) -> total or -1"},
     {"scan", hp_scan, METH_O, "scan(list) -> (total code points, all_ascii)"},
     {"fill", hp_fill, METH_VARARGS, "fill(list, blob, offsets, width)"},
     {NULL, NULL, 0, NULL}};

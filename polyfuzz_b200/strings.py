@@ -23,6 +23,12 @@ def pack_utf32(strings):
 def ngram_slot_bounds(offsets, lo, hi):
     """Upper bound of n-gram occurrences per string (before cleaning): sum_n max(0, len-n+1);
     returns (slots int64[n], occ_ptr int64[n+1])."""
+    hp = _hostpack()
+    if hp is not None and hasattr(hp, "slots") and offsets.dtype == np.int64 and offsets.flags.c_contiguous and len(offsets) > 0:
+        n = len(offsets) - 1
+        slots = np.empty(n, dtype=np.int64); occ = np.empty(n + 1, dtype=np.int64)
+        hp.slots(offsets, slots, occ, int(lo), int(hi))           # one C pass
+        return slots, occ
     lens = np.diff(offsets)
     slots = np.zeros_like(lens)
     for n in range(lo, hi + 1):
@@ -55,6 +61,7 @@ def _hostpack():
 
 
 _HP = False
+_BYTES_PER_STRING = 40.0     # running guess for the one-pass ASCII packer
 
 
 def pack_strings(strings):
@@ -64,6 +71,18 @@ def pack_strings(strings):
     n = len(strings)
     hp = _hostpack()
     if hp is not None and n and isinstance(strings, (list, tuple)):
+        if hasattr(hp, "fill_ascii"):
+            # the common case in ONE pass: a pure-ASCII list that fits a guessed byte buffer (the last list's bytes per string + slack)
+            global _BYTES_PER_STRING
+            guess = int(n * _BYTES_PER_STRING) + 4096
+            big = np.empty(guess, dtype=np.uint8)
+            offsets = np.empty(n + 1, dtype=np.int64)
+            total = hp.fill_ascii(strings, big, offsets)          # TypeError on non-str
+            if total >= 0:
+                _BYTES_PER_STRING = max(8.0, 1.25 * total / n)
+                blob = big[:total] if 2 * total >= guess else big[:total].copy()
+                return (blob if total else np.zeros(0, np.uint8)), offsets, None
+            _BYTES_PER_STRING = min(256.0, 2.0 * _BYTES_PER_STRING)
         total, ascii_only = hp.scan(strings)                  # one C pass; TypeError on non-str
         blob = np.empty(max(total, 1), dtype=np.uint8 if ascii_only else np.uint32)
         offsets = np.empty(n + 1, dtype=np.int64)
