@@ -55,6 +55,29 @@ def test_slot_bounds_cover_every_ngram(rng):
     assert occ[-1] == slots.sum() and occ[0] == 0
 
 
+def test_c_packer_one_pass_paths_equal_the_numpy_paths(monkeypatch):
+    """fill_ascii (one pass, guessed buffer) must fall back cleanly -- buffer too small, a non-ASCII string in the middle -- and
+    the C slot bounds must equal the numpy expression for every n-gram range."""
+    from polyfuzz_b200 import strings, synth
+    assert hasattr(strings._hostpack(), "fill_ascii") and hasattr(strings._hostpack(), "slots")
+    names = synth.company_names(3000, seed=7)
+    ref_b, ref_o = pack_utf32(names)
+    for guess in (1.0, 40.0, 4000.0):                       # too small (falls back to scan + fill) / typical / far too large (copies down)
+        monkeypatch.setattr(strings, "_BYTES_PER_STRING", guess)
+        b, o, _ = strings.pack_strings(names)
+        assert b.dtype == np.uint8 and np.array_equal(b.astype(np.uint32), ref_b) and np.array_equal(o, ref_o)
+    mixed = names[:100] + ["caf\u00e9 ltd"] + names[100:200]
+    b, o, _ = strings.pack_strings(mixed)
+    rb, ro = pack_utf32(mixed)
+    assert b.dtype == np.uint32 and np.array_equal(b, rb) and np.array_equal(o, ro)
+    for rng_ in ((1, 1), (1, 3), (3, 3), (2, 5), (3, 6)):
+        s1, o1 = ngram_slot_bounds(ref_o, *rng_)
+        monkeypatch.setattr(strings, "_HP", None)            # numpy path
+        s2, o2 = ngram_slot_bounds(ref_o, *rng_)
+        monkeypatch.undo()
+        assert np.array_equal(s1, s2) and np.array_equal(o1, o2)
+
+
 def test_assemble_matches_equals_reference_tail_restatement():
     rng = np.random.default_rng(0)
     frm = [f"f{i}" for i in range(50)]; to = [f"t{i}" for i in range(20)]
