@@ -282,11 +282,12 @@ int pfz_dense_cos_topk(const void *x_bf16, const void *y_bf16, int32_t n_from, i
  *   lens_pos int32[k*n + 1]  on return the EXCLUSIVE prefix of the matched strings' byte lengths (last entry = total bytes)
  *   bitmap  uint32[k * ceil(n/32)]   Arrow validity bits (bit i of column r)
  *   ws: >= pfz_scan_ws_bytes(k*n + 1) bytes.
- * then, with the total known to the caller: offsets int32[k*(n+1)] (relative to each column's start) and the UTF-8 bytes.   */
+ * then, with the total known to the caller: offsets int64[k*(n+1)] (relative to each column's start: Arrow large_string, what
+ * pandas' Arrow-backed str dtype holds) and the UTF-8 bytes.   */
 int pfz_frame_tail_count(const int32_t *top_idx, const double *top_val, int32_t n, int32_t k, const int64_t *to_offsets, double *sims,
                          int32_t *lens_pos, uint32_t *bitmap, void *ws, void *stream);
 int pfz_frame_tail_copy(const int32_t *top_idx, int32_t n, int32_t k, const int32_t *to_blob, const int64_t *to_offsets, const int32_t *pos,
-                        int32_t *offsets, uint8_t *data, void *stream);
+                        int64_t *offsets, uint8_t *data, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,7 @@
 // pfz_assemble.cu -- K5: the frame tail on the device.  From the top-k arrays to the COLUMNS of the result frame:
 // per rank r the rounded similarities, the validity bitmap and the matched to-strings gathered into one Arrow string
-// column (int32 offsets + UTF-8 bytes), ready to be wrapped zero-copy by the host.
+// column (int64 offsets -- Arrow large_string, the layout pandas' str dtype holds, so that the host wraps it without a cast --
+// + UTF-8 bytes), ready to be wrapped zero-copy by the host.
 //
 // Replaces the tail of polyfuzz/models/_utils.py:104-125: `matches = [[to_list[idx] for idx in indices[:, i]] ...]`,
 // the (1 + 2k) x n unicode ndarray, the 3-decimal rounding (:102 / :143) and the `Similarity < 0.001 -> 0, To -> None`
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(256) tail_count_kernel(const int32_t *__restri
 // one warp per entry: copy the matched string's code points (ASCII) as bytes; offsets relative to the column start
 __global__ void __launch_bounds__(256) tail_copy_kernel(const int32_t *__restrict__ idx, int n, int k, const int32_t *__restrict__ to_blob,
                                                         const int64_t *__restrict__ to_off, const int32_t *__restrict__ pos,
-                                                        int32_t *__restrict__ offsets, uint8_t *__restrict__ data) {
+                                                        int64_t *__restrict__ offsets, uint8_t *__restrict__ data) {
     const int lane = lane_id();
     const int64_t n_ent = (int64_t)n * k;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -77,7 +78,7 @@ int pfz_frame_tail_count(const int32_t *top_idx, const double *top_val, int32_t 
 }
 
 int pfz_frame_tail_copy(const int32_t *top_idx, int32_t n, int32_t k, const int32_t *to_blob, const int64_t *to_offsets, const int32_t *pos,
-                        int32_t *offsets, uint8_t *data, void *stream) {
+                        int64_t *offsets, uint8_t *data, void *stream) {
     if (n <= 0 || k <= 0) return 0;
     const int64_t n_ent = (int64_t)n * k;
     int grid = (int)((n_ent * 32 + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;

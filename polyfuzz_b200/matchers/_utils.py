@@ -146,7 +146,7 @@ def assemble_matches_device(from_arrow, to_blob, to_off, top_idx, top_val) -> pd
     ws = _ws(_lib.load().pfz_scan_ws_bytes(k * n + 1))
     _lib.call("pfz_frame_tail_count", _p(top_idx), _p(top_val), n, k, _p(to_off), _p(sims), _p(pos), _p(bitmap), _p(ws), _stream())
     total = int(pos[-1].item())                               # the one host sync of the tail (everything before it is done by then)
-    offsets = torch.empty(k * (n + 1), dtype=torch.int32, device=dev)
+    offsets = torch.empty(k * (n + 1), dtype=torch.int64, device=dev)           # large_string offsets: pandas wraps them without a cast
     data = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
     _lib.call("pfz_frame_tail_copy", _p(top_idx), n, k, _p(to_blob), _p(to_off), _p(pos), _p(offsets), _p(data), _stream())
     # one buffer, one D2H: [sims | offsets | bitmap | data]
@@ -166,13 +166,13 @@ def assemble_matches_device(from_arrow, to_blob, to_off, top_idx, top_val) -> pd
     LAST_TAIL["d2h_bytes"], LAST_TAIL["device"] = int(host.nbytes) + 4, True
     o = np.cumsum([0] + sizes)
     h_sims = host[o[0]:o[1]].view(np.float64).reshape(k, n)
-    h_off = host[o[1]:o[2]].view(np.int32).reshape(k, n + 1)
+    h_off = host[o[1]:o[2]].view(np.int64).reshape(k, n + 1)
     h_bm = host[o[2]:o[3]].reshape(k, nw * 4)
     h_data = host[o[3]:o[4]]
-    col0 = np.concatenate([[0], np.cumsum(h_off[:, n].astype(np.int64))])     # byte range of every column in `data`
-    cols = {"From": pd.Series(AT(from_arrow, dtype=dt), copy=False)}
+    col0 = np.concatenate([[0], np.cumsum(h_off[:, n])])                      # byte range of every column in `data`
+    cols = {"From": AT(from_arrow, dtype=dt)}
     for r in range(k):
-        arr = pa.StringArray.from_buffers(n, pa.py_buffer(h_off[r]), pa.py_buffer(h_data[col0[r]:col0[r + 1]]), pa.py_buffer(h_bm[r]))
-        cols["To" if r == 0 else f"To_{r + 1}"] = pd.Series(AT(arr, dtype=dt), copy=False)
+        arr = pa.LargeStringArray.from_buffers(n, pa.py_buffer(h_off[r]), pa.py_buffer(h_data[col0[r]:col0[r + 1]]), pa.py_buffer(h_bm[r]))
+        cols["To" if r == 0 else f"To_{r + 1}"] = AT(arr, dtype=dt)
         cols["Similarity" if r == 0 else f"Similarity_{r + 1}"] = h_sims[r]
     return pd.DataFrame(cols, copy=False)
